@@ -1,0 +1,168 @@
+/*
+ * smrf_b200.h -- C ABI of libsmrf_b200.so: the B200 (sm_100a) implementation of
+ * the SMRF ground-classification hot path of thomaspingel/neilpy.
+ *
+ * The reference has no FFI of its own: its boundary for this path is the Python
+ * call surface re-exported at neilpy/__init__.py:1
+ *     smrf                     neilpy/neilpy.py:1685-1808
+ *     create_dem               neilpy/neilpy.py:1110-1166
+ *     inpaint_nans_by_springs  neilpy/neilpy.py:1227-1271
+ *     progressive_filter       neilpy/neilpy.py:1659-1680
+ * Each entry point below replaces the arithmetic of the reference lines it
+ * cites; the Python mirror (neilpy_b200/api.py) keeps the reference signatures
+ * and binds these symbols through ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in _host.  The caller owns every buffer (inputs,
+ *     outputs, workspaces); the library never allocates, frees or retains.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     Calls are asynchronous on that stream except where stated.
+ *   - return value: 0 = ok, < 0 = argument error (SMRF_E_*), > 0 = cudaError_t.
+ *     smrf_last_error() returns a per-thread description of the last failure.
+ *   - `dtype` selects the grid element type: SMRF_F32 (throughput mode) or
+ *     SMRF_F64 (parity mode, the reference's own float64).
+ *   - grids are row-major [ny][nx], row 0 = north (as the reference's I[r, c]).
+ *   - masks are uint8 (0/1), one byte per cell or point (numpy bool layout).
+ */
+#ifndef SMRF_B200_H
+#define SMRF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMRF_F32 0
+#define SMRF_F64 1
+
+/* point stream layouts */
+#define SMRF_PTS_SOA_F64 0 /* three separate double arrays x, y, z (the reference's own) */
+#define SMRF_PTS_XYZW_F32 1 /* one interleaved float4 array (x, y, z, unused); `x` is its base, y = z = NULL */
+#define SMRF_PTS_SOA_F32 2 /* three separate float arrays */
+
+#define SMRF_BIN_MIN 0
+#define SMRF_BIN_MAX 1
+
+#define SMRF_E_ARG (-1)      /* null pointer / bad enum / bad size */
+#define SMRF_E_WORKSPACE (-2) /* workspace too small */
+#define SMRF_E_UNSUPPORTED (-3)
+
+int smrf_abi_version(void);
+const char* smrf_last_error(void);
+/* name of the opening implementation a call with these parameters would use
+ * ("march_f32_w<=18", "tile_generic", ...) -- for logs and the bench JSON. */
+const char* smrf_open_variant(int dtype, int window);
+
+/* ---- create_dem: extent -------------------------------------- neilpy.py:1117-1124
+ * min/max of x and y (np.min / np.max).  out4 = {min x, max x, min y, max y} as
+ * doubles, nonfinite[0] = number of non-finite x or y (the reference would fail on
+ * them in np.arange / np.ravel_multi_index).  `scratch` holds 4 int64 keys. */
+int smrf_extent(const void* x, const void* y, int64_t n, int point_fmt,
+                double* out4, int64_t* nonfinite, int64_t* scratch4, void* stream);
+
+/* ---- create_dem: binning ------------------------------------- neilpy.py:1136-1161
+ * Replaces ~t*(x,y) -> floor -> ravel_multi_index -> groupby().min()/max() -> scatter.
+ * inv6 = {ra, rb, rc, rd, re, rf}: the inverse affine exactly as the `affine`
+ * package computes it on the host (col = x*ra + y*rb + rc, row = x*rd + y*re + rf,
+ * evaluated left to right in float64 without FMA contraction).
+ *   smrf_bin_init       : fill `grid` (ny*nx elements of `dtype`) with the empty key
+ *   smrf_bin_accumulate : atomic min/max of order-preserving keys; may be called
+ *                         repeatedly (chunks / several point sources).  NaN z is
+ *                         skipped (pandas skips NaN).  Points that fall outside the
+ *                         grid are counted in out_of_range[0] (the reference raises
+ *                         ValueError from np.ravel_multi_index).
+ *   smrf_bin_finalize   : keys -> values in place, untouched cells -> NaN,
+ *                         empty[i] = 1 for them (neilpy.py:1742 is_empty_cell). */
+int smrf_bin_init(void* grid, int64_t ny, int64_t nx, int dtype, int bin_type, void* stream);
+int smrf_bin_accumulate(const void* x, const void* y, const void* z, int64_t n, int point_fmt,
+                        const double* inv6_host, void* grid, int64_t ny, int64_t nx, int dtype,
+                        int bin_type, int64_t* out_of_range, void* stream);
+int smrf_bin_finalize(void* grid, uint8_t* empty, int64_t ny, int64_t nx, int dtype, int bin_type,
+                      void* stream);
+
+/* ---- inpaint_nans_by_springs --------------------------------- neilpy.py:1227-1271
+ * Discrete harmonic fill of the NaN cells of `grid` (in place): for every NaN cell
+ * deg*u - sum(NaN nbrs u) = sum(known nbrs a), deg = number of in-grid 4-neighbours
+ * (the normal equations of the reference's spring system).  Solved in float64 by
+ * preconditioned conjugate gradients entirely in HBM; stops when the
+ * max-norm of the residual is <= tol (metres) or after max_iter iterations.
+ * A grid with no NaN is returned unchanged; an all-NaN grid becomes zeros (the
+ * minimum-norm answer LSQR gives).  `unknown` (optional, may be NULL) receives the
+ * NaN mask.  info_host[0] = iterations, info_host[1] = final residual max-norm,
+ * info_host[2] = number of unknown cells.  Synchronises `stream`. */
+size_t smrf_inpaint_workspace_bytes(int64_t ny, int64_t nx);
+int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown,
+                 void* workspace, size_t workspace_bytes, double tol, int max_iter,
+                 double* info_host, void* stream);
+
+/* ---- progressive_filter -------------------------------------- neilpy.py:1659-1680
+ * For each radius windows_host[i] (in order): this = opening(last, disk(w));
+ * new = (last - this) > thresholds_host[i] (float64 compare); mask |= new;
+ * when_dropped[new] = i (optional); last = this.  disk(w) = {dx^2+dy^2 <= w^2};
+ * borders ignore out-of-image samples (== scipy.ndimage 'reflect' for a disk).
+ *   surface  : ny*nx elements, the input Z; never written (the reference works on a copy)
+ *   workspace: smrf_open_workspace_bytes() bytes (ping-pong surfaces + scratch)
+ *   mask     : uint8 ny*nx, OR-accumulated (caller zeroes it for a fresh filter)
+ *   negate   : open -Z instead of Z (the low-outlier pass, neilpy.py:1744); one window only
+ *   last_out : optional ny*nx elements receiving the last window's opening (NULL to skip)
+ * thresholds are computed by the caller exactly as the reference does
+ * (slope_threshold * (windows * cellsize), neilpy.py:1661). */
+size_t smrf_open_workspace_bytes(int64_t ny, int64_t nx, int dtype, int max_window);
+int smrf_progressive_open(const void* surface, void* workspace, size_t workspace_bytes, uint8_t* mask,
+                          uint8_t* when_dropped, int64_t ny, int64_t nx, int dtype,
+                          const int32_t* windows_host, const double* thresholds_host, int n_windows,
+                          int negate, void* last_out, void* stream);
+/* one window, out of place: `out` = opening(in, disk(window)); mask/when_dropped as above
+ * (either may be NULL); `tmp` = ny*nx elements.  Only rows [row_lo,row_hi) of out/mask are
+ * written: with row-band sharding the halo rows outside are inputs only (pass 0, ny
+ * otherwise).  Building block of smrf_progressive_open and of the multi-GPU driver. */
+int smrf_open_window(const void* in, void* out, void* tmp, uint8_t* mask, uint8_t* when_dropped,
+                     int64_t ny, int64_t nx, int dtype, int window, double threshold, int window_index,
+                     int negate, int64_t row_lo, int64_t row_hi, void* stream);
+/* brute-force disk opening (|disk| loads per cell); the in-library cross-check of the fast kernels */
+int smrf_open_window_bruteforce(const void* in, void* out, void* tmp, int64_t ny, int64_t nx, int dtype,
+                                int window, void* stream);
+
+/* ---- mask merge + punch -------------------------------------- neilpy.py:1762-1763
+ * object = empty | low | obj (written to `object_cells`); grid[object] = NaN. */
+int smrf_merge_punch(void* grid, const uint8_t* empty, const uint8_t* low, const uint8_t* obj,
+                     uint8_t* object_cells, int64_t ny, int64_t nx, int dtype, void* stream);
+
+/* ---- slope ---------------------------------------------------- neilpy.py:1785-1786
+ * S = sqrt(gy^2 + gx^2), gy, gx = np.gradient(Z, cellsize) (central differences,
+ * one-sided at the edges).  float64 arithmetic, stored as `dtype`. */
+int smrf_slope(const void* grid, void* slope, int64_t ny, int64_t nx, int dtype, double cellsize,
+               void* stream);
+
+/* ---- RectBivariateSpline(kx=ky=3, s=0) ------------------------ neilpy.py:1768-1774,1788-1790
+ * B-spline coefficients of the interpolating (not-a-knot) bicubic spline through the
+ * grid values at the cell centres 0.5, 1.5, ...  The banded collocation system of each
+ * axis depends only on its length; the caller factors it once on the host
+ * (neilpy_b200.spline.notaknot_factors) and passes, per axis, a DEVICE array of 5*n
+ * doubles {l1, l2, 1/pivot, u1, u2} (banded LU without pivoting; row_factors for the
+ * ny-long axis, col_factors for the nx-long one).  Intermediates are float64 in
+ * `workspace`.  `coef` may alias `grid`.  ny, nx >= 4 (FITPACK raises otherwise). */
+size_t smrf_spline_workspace_bytes(int64_t ny, int64_t nx);
+int smrf_spline_prefilter(const void* grid, void* coef, int64_t ny, int64_t nx, int dtype,
+                          const double* row_factors, const double* col_factors, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* ---- interpolate + classify ----------------------------------- neilpy.py:1772-1795
+ * For every point: (c, r) = ~t*(x, y); elevation = spline(Zpro).ev(r, c);
+ * slope = spline(S).ev(r, c) (arguments clamped to the centre range as FITPACK's bispeu
+ * does); is_object = |elevation - z| > elevation_threshold + elevation_scaler*slope.
+ * Optional outputs (may be NULL): elevation, slope_out (float64 per point),
+ * when_dropped_pt = drop_raster[round(r), round(c)] if drop_raster != NULL. */
+int smrf_classify(const void* x, const void* y, const void* z, int64_t n, int point_fmt,
+                  const double* inv6_host, const void* coef_z, const void* coef_s, int64_t ny,
+                  int64_t nx, int dtype, double elevation_threshold, double elevation_scaler,
+                  uint8_t* is_object, double* elevation, double* slope_out,
+                  const uint8_t* drop_raster, uint8_t* when_dropped_pt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMRF_B200_H */

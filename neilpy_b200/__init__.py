@@ -1,0 +1,12 @@
+"""neilpy_b200 -- the SMRF ground-classification path of thomaspingel/neilpy on B200.
+
+Drop-in for `from neilpy import smrf, create_dem, progressive_filter,
+inpaint_nans_by_springs` (neilpy/__init__.py:1); everything else in neilpy is out of scope.
+Compute lives in libsmrf_b200.so (hand-written CUDA for sm_100a behind a C ABI,
+include/smrf_b200.h); build it with `python -m neilpy_b200.build`.
+"""
+from .affine import Affine
+from .api import create_dem, inpaint_nans_by_springs, progressive_filter, smrf
+
+__all__ = ['smrf', 'create_dem', 'progressive_filter', 'inpaint_nans_by_springs', 'Affine']
+__version__ = '0.1.0'

@@ -1,0 +1,446 @@
+"""CPU oracle for the SMRF hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file restates, in numpy/scipy, the four reference functions on the SMRF
+path of thomaspingel/neilpy so that the CUDA path can be checked against them:
+
+    create_dem                 neilpy/neilpy.py:1110-1166
+    unique_rows                neilpy/neilpy.py:1221-1224
+    inpaint_nans_by_springs    neilpy/neilpy.py:1227-1271
+    progressive_filter         neilpy/neilpy.py:1659-1680
+    smrf                       neilpy/neilpy.py:1685-1808
+
+The reference itself cannot be imported in this image (matplotlib, rasterio,
+affine, skimage, ... are absent -- SURVEY.md F1), so three third-party pieces are
+restated from their published definitions:
+
+    skimage.morphology.disk(w)          -> `disk`            (x^2 + y^2 <= w^2)
+    skimage.morphology.opening(img,fp)  -> grey_erosion then grey_dilation of
+                                           scipy.ndimage with the same footprint
+                                           (skimage >=0.19 dispatches to exactly these)
+    rasterio.transform.from_origin, ~t, t*(x,y)
+                                        -> `Affine6` (the 6-float formulas of the
+                                           `affine` package: __invert__, __mul__)
+
+Everything else (pandas groupby-min, scipy.sparse + lsqr, RectBivariateSpline,
+np.gradient) is called exactly as the reference calls it.
+
+Parity pin: `smrf` on sample_data/samp12.txt with the notebook parameters
+reproduces the reference notebook's printed output (Type I 2.00566304861 %,
+Type II 4.12498595032 %, total 3.09100328095 %, kappa 93.8109576375 %) digit for
+digit -- tests/test_oracle_golden.py.  At every third-party boundary the
+reference's own tests pin nothing; this restatement run in this image is the
+ground truth there ("parity unpinned" per stage, pinned end to end).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  The product (neilpy_b200) never does.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import scipy.ndimage as ndi
+from scipy import interpolate, sparse
+from scipy.sparse import linalg as splinalg
+
+
+# --------------------------------------------------------------------------
+# third-party restatements
+# --------------------------------------------------------------------------
+class Affine6:
+    """The six coefficients (a, b, c, d, e, f) of affine.Affine, with the
+    arithmetic of its __invert__ and __mul__ (neilpy.py:1141-1142, :1772)."""
+
+    def __init__(self, a, b, c, d, e, f):
+        self.coeffs = (float(a), float(b), float(c), float(d), float(e), float(f))
+
+    @classmethod
+    def from_origin(cls, west, north, xsize, ysize):
+        # rasterio.transform.from_origin = translation(west, north) * scale(xsize, -ysize)
+        return cls(xsize, 0.0, west, 0.0, -ysize, north)
+
+    def __getitem__(self, i):
+        return (self.coeffs + (0.0, 0.0, 1.0))[i]
+
+    def __invert__(self):
+        a, b, c, d, e, f = self.coeffs
+        idet = 1.0 / (a * e - b * d)
+        ra = e * idet
+        rb = -b * idet
+        rd = -d * idet
+        re = a * idet
+        return Affine6(ra, rb, -c * ra - f * rb, rd, re, -c * rd - f * re)
+
+    def __mul__(self, other):
+        sa, sb, sc, sd, se, sf = self.coeffs
+        vx, vy = other
+        return (vx * sa + vy * sb + sc, vx * sd + vy * se + sf)
+
+    def __repr__(self):
+        return "Affine6(%r, %r, %r,\n        %r, %r, %r)" % self.coeffs
+
+
+def disk(radius):
+    """skimage.morphology.disk: (2r+1)^2 uint8, 1 where dx^2+dy^2 <= r^2."""
+    L = np.arange(-radius, radius + 1)
+    X, Y = np.meshgrid(L, L)
+    return np.array((X ** 2 + Y ** 2) <= radius ** 2, dtype=np.uint8)
+
+
+def opening(image, footprint):
+    """skimage.morphology.opening for an ndarray footprint."""
+    eroded = ndi.grey_erosion(image, footprint=footprint)
+    return ndi.grey_dilation(eroded, footprint=footprint)
+
+
+# --------------------------------------------------------------------------
+# neilpy.py:1110-1166
+# --------------------------------------------------------------------------
+def create_dem(x, y, z, cellsize=1, bin_type='max', inpaint=False, edges=None):
+    floor2 = lambda x, v: v * np.floor(x / v)
+    ceil2 = lambda x, v: v * np.ceil(x / v)
+
+    if edges is None:
+        xedges = np.arange(floor2(np.min(x), cellsize) - .5 * cellsize,
+                           ceil2(np.max(x), cellsize) + 1.5 * cellsize, cellsize)
+        yedges = np.arange(ceil2(np.max(y), cellsize) + .5 * cellsize,
+                           floor2(np.min(y), cellsize) - 1.5 * cellsize, -cellsize)
+    else:
+        xedges = edges[0]
+        yedges = edges[1]
+        out_of_range = (x < xedges[0]) | (x > xedges[-1]) | (y > yedges[0]) | (y < yedges[-1])
+        x = x[~out_of_range]
+        y = y[~out_of_range]
+        z = z[~out_of_range]
+        cellsize = np.abs(xedges[1] - xedges[0])
+
+    nx, ny = len(xedges) - 1, len(yedges) - 1
+
+    I = np.empty(nx * ny)
+    I[:] = np.nan
+
+    t = Affine6.from_origin(xedges[0], yedges[0], cellsize, cellsize)
+    c, r = ~t * (x, y)
+    c, r = np.floor(c).astype(np.int64), np.floor(r).astype(np.int64)
+
+    mx = pd.DataFrame({'i': np.ravel_multi_index((r, c), (ny, nx)), 'z': z}).groupby('i')
+    del c, r
+    if bin_type == 'max':
+        mx = mx.max()
+    elif bin_type == 'min':
+        mx = mx.min()
+    else:
+        raise ValueError('This type not supported.')
+
+    I.flat[mx.index.values] = mx.values
+    I = I.reshape((ny, nx))
+
+    if inpaint == True:
+        I = inpaint_nans_by_springs(I)
+
+    return I, t
+
+
+# --------------------------------------------------------------------------
+# neilpy.py:1221-1271
+# --------------------------------------------------------------------------
+def unique_rows(a):
+    a = np.ascontiguousarray(a)
+    unique_a = np.unique(a.view([('', a.dtype)] * a.shape[1]))
+    return unique_a.view(a.dtype).reshape((unique_a.shape[0], a.shape[1]))
+
+
+def inpaint_nans_by_springs(A, inplace=False, neighbors=4, return_info=False):
+    m, n = np.shape(A)
+    nanmat = np.isnan(A)
+
+    nan_list = np.flatnonzero(nanmat)
+    known_list = np.flatnonzero(~nanmat)
+
+    r, c = np.unravel_index(nan_list, (m, n))
+
+    num_neighbors = neighbors
+    neighbors = np.array([[0, 1], [0, -1], [-1, 0], [1, 0]])
+    neighbors = np.vstack([np.vstack((r + i[0], c + i[1])).T for i in neighbors])
+    del r, c
+
+    springs = np.tile(nan_list, num_neighbors)
+    good_rows = (np.all(neighbors >= 0, 1)) & (neighbors[:, 0] < m) & (neighbors[:, 1] < n)
+
+    neighbors = np.ravel_multi_index((neighbors[good_rows, 0], neighbors[good_rows, 1]), (m, n))
+    springs = springs[good_rows]
+
+    springs = np.vstack((springs, neighbors)).T
+    del neighbors, good_rows
+
+    springs = np.sort(springs, axis=1)
+    springs = unique_rows(springs)
+
+    n_springs = np.shape(springs)[0]
+
+    i = np.tile(np.arange(n_springs), 2)
+    springs = springs.T.ravel()
+    data = np.hstack((np.ones(n_springs, dtype=np.int8), -1 * np.ones(n_springs, dtype=np.int8)))
+    springs = sparse.coo_matrix((data, (i, springs)), (n_springs, m * n), dtype=np.int8).tocsr()
+    del i, data
+
+    rhs = -springs[:, known_list] * A[np.unravel_index(known_list, (m, n))]
+    sol = splinalg.lsqr(springs[:, nan_list], rhs)
+    results = sol[0]
+
+    if inplace:
+        A[np.unravel_index(nan_list, (m, n))] = results
+        return None
+    B = A.copy()
+    B[np.unravel_index(nan_list, (m, n))] = results
+    if return_info:
+        return B, {'lsqr_iterations': int(sol[2]), 'lsqr_istop': int(sol[1])}
+    return B
+
+
+def harmonic_fill_exact(A):
+    """Exact (sparse-direct) solution of the spring system that
+    inpaint_nans_by_springs hands to LSQR: for every NaN cell i,
+    deg(i)*u_i - sum_{NaN nbrs} u_j = sum_{known nbrs} a_k, deg = number of
+    in-grid 4-neighbours.  Used to state how far LSQR (atol=btol=1e-6) and the
+    CUDA solver each sit from the true minimiser."""
+    A = np.asarray(A, dtype=np.float64)
+    m, n = A.shape
+    nan = np.isnan(A)
+    if not nan.any():
+        return A.copy()
+    idx = -np.ones(m * n, dtype=np.int64)
+    nan_list = np.flatnonzero(nan)
+    idx[nan_list] = np.arange(nan_list.size)
+    r, c = np.unravel_index(nan_list, (m, n))
+    rows, cols, vals = [], [], []
+    deg = np.zeros(nan_list.size)
+    rhs = np.zeros(nan_list.size)
+    flatA = A.ravel()
+    for dr, dc in ((0, 1), (0, -1), (-1, 0), (1, 0)):
+        rr, cc = r + dr, c + dc
+        ok = (rr >= 0) & (rr < m) & (cc >= 0) & (cc < n)
+        deg += ok
+        nb = np.where(ok, rr * n + cc, 0)
+        nb_nan = ok & nan.ravel()[nb]
+        nb_known = ok & ~nan.ravel()[nb]
+        rows.append(np.flatnonzero(nb_nan))
+        cols.append(idx[nb[nb_nan]])
+        vals.append(-np.ones(int(nb_nan.sum())))
+        rhs += np.where(nb_known, flatA[nb], 0.0)
+    rows.append(np.arange(nan_list.size))
+    cols.append(np.arange(nan_list.size))
+    vals.append(deg)
+    L = sparse.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                          shape=(nan_list.size, nan_list.size))
+    # components with no known neighbour anywhere are singular; LSQR returns the
+    # minimum-norm solution (0 for an all-NaN grid).  Regularise those only.
+    ncomp, lab = sparse.csgraph.connected_components(L, directed=False)
+    has_known = np.zeros(ncomp, dtype=bool)
+    np.logical_or.at(has_known, lab, rhs != 0)
+    touches = np.zeros(ncomp, dtype=bool)
+    known_nb = np.zeros(nan_list.size, dtype=bool)
+    for dr, dc in ((0, 1), (0, -1), (-1, 0), (1, 0)):
+        rr, cc = r + dr, c + dc
+        ok = (rr >= 0) & (rr < m) & (cc >= 0) & (cc < n)
+        nb = np.where(ok, rr * n + cc, 0)
+        known_nb |= ok & ~nan.ravel()[nb]
+    np.logical_or.at(touches, lab, known_nb)
+    free = ~touches[lab]
+    if free.any():
+        L = L + sparse.diags(free.astype(np.float64))
+    u = splinalg.spsolve(L.tocsc(), rhs)
+    B = A.copy()
+    B.ravel()[nan_list] = u
+    return B
+
+
+# --------------------------------------------------------------------------
+# neilpy.py:1659-1680
+# --------------------------------------------------------------------------
+def progressive_filter(Z, windows, cellsize=1, slope_threshold=.15, return_when_dropped=False,
+                       stage_hook=None):
+    last_surface = Z.copy()
+    elevation_thresholds = slope_threshold * (windows * cellsize)
+    is_object_cell = np.zeros(np.shape(Z), dtype=bool)
+    if return_when_dropped:
+        when_dropped = np.zeros(np.shape(Z), dtype=np.uint8)
+    for i, window in enumerate(windows):
+        elevation_threshold = elevation_thresholds[i]
+        # neilpy.py:1667-1669 builds a 3x3 square for window==1 but :1670 then
+        # ignores it and calls disk(window): radius 1 is the 5-pixel cross.
+        this_surface = opening(last_surface, disk(window))
+        new_obj = last_surface - this_surface > elevation_threshold
+        is_object_cell = (is_object_cell) | (new_obj)
+        if return_when_dropped:
+            when_dropped[new_obj] = i
+        if stage_hook is not None:
+            stage_hook(i, window, this_surface, new_obj)
+        if i < len(windows) and len(windows) > 1:
+            last_surface = this_surface.copy()
+    if return_when_dropped:
+        return is_object_cell, when_dropped
+    else:
+        return is_object_cell
+
+
+# --------------------------------------------------------------------------
+# neilpy.py:1685-1808
+# --------------------------------------------------------------------------
+def smrf(x, y, z, cellsize=1, windows=5, slope_threshold=.15, elevation_threshold=.5,
+         elevation_scaler=1.25, low_filter_slope=5, low_outlier_fill=False,
+         return_extras=False, stages=None):
+    """`stages`, if a dict, receives every intermediate of the run (the
+    per-stage golden vectors the CUDA parity tests consume)."""
+    if np.isscalar(windows):
+        windows = np.arange(windows) + 1
+
+    Zmin, t = create_dem(x, y, z, cellsize=cellsize, bin_type='min')
+    is_empty_cell = np.isnan(Zmin)
+    if stages is not None:
+        stages['Zmin_binned'] = Zmin.copy()
+    Zmin = inpaint_nans_by_springs(Zmin)
+    if stages is not None:
+        stages['Zmin_inpainted'] = Zmin.copy()
+    low_outliers = progressive_filter(-Zmin, np.array([1]), cellsize, slope_threshold=low_filter_slope)
+
+    if low_outlier_fill:
+        Zmin[low_outliers] = np.nan
+        Zmin = inpaint_nans_by_springs(Zmin)
+    if stages is not None:
+        stages['low_outliers'] = low_outliers.copy()
+        stages['Zmin_filtered'] = Zmin.copy()
+
+    if return_extras:
+        object_cells, drop_raster = progressive_filter(Zmin, windows, cellsize, slope_threshold,
+                                                       return_when_dropped=True)
+    else:
+        object_cells = progressive_filter(Zmin, windows, cellsize, slope_threshold)
+    if stages is not None:
+        stages['progressive_cells'] = object_cells.copy()
+
+    Zpro = Zmin
+    del Zmin
+    object_cells = is_empty_cell | low_outliers | object_cells
+    Zpro[object_cells] = np.nan
+    if stages is not None:
+        stages['Zpro_punched'] = Zpro.copy()
+    Zpro = inpaint_nans_by_springs(Zpro)
+
+    col_centers = np.arange(0.5, Zpro.shape[1] + .5)
+    row_centers = np.arange(0.5, Zpro.shape[0] + .5)
+
+    c, r = ~t * (x, y)
+    f1 = interpolate.RectBivariateSpline(row_centers, col_centers, Zpro)
+    elevation_values = f1.ev(r, c)
+
+    if return_extras:
+        when_dropped = drop_raster[np.round(r).astype(int), np.round(c).astype(int)]
+
+    gy, gx = np.gradient(Zpro, cellsize)
+    S = np.sqrt(gy ** 2 + gx ** 2)
+    del gy, gx
+    f2 = interpolate.RectBivariateSpline(row_centers, col_centers, S)
+    slope_values = f2.ev(r, c)
+
+    required_value = elevation_threshold + (elevation_scaler * slope_values)
+    is_object_point = np.abs(elevation_values - z) > required_value
+
+    if stages is not None:
+        stages.update(Zpro=Zpro.copy(), object_cells=object_cells.copy(), S=S.copy(),
+                      r=np.asarray(r), c=np.asarray(c),
+                      elevation_values=np.asarray(elevation_values),
+                      slope_values=np.asarray(slope_values),
+                      is_object_point=np.asarray(is_object_point), t=t.coeffs)
+    del S
+
+    if return_extras == True:
+        extras = {}
+        extras['above_ground_height'] = z - elevation_values
+        extras['drop_raster'] = drop_raster
+        extras['when_dropped'] = when_dropped
+
+    if return_extras == False:
+        return Zpro, t, object_cells, is_object_point
+    else:
+        return Zpro, t, object_cells, is_object_point, extras
+
+
+# --------------------------------------------------------------------------
+# deterministic synthetic cloud -- shared by tests and bench
+# --------------------------------------------------------------------------
+def terrain(x, y):
+    tp = 2.0 * np.pi
+    return (30.0 * np.sin(tp * x / 2000.0 + .3) * np.cos(tp * y / 1700.0 + 1.1)
+            + 8.0 * np.sin(tp * x / 400.0 + 2.0) * np.sin(tp * y / 370.0 + .7)
+            + 2.0 * np.sin(tp * x / 80.0 + .5) * np.cos(tp * y / 90.0 + .2)
+            + 0.02 * x + 100.0)
+
+
+def _lattice_rand(ix, iy, salt):
+    """Stateless per-lattice-cell uniform [0,1) (so any sub-region of the plane
+    generates the same buildings regardless of how points are sliced)."""
+    h = (ix.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+         ^ (iy.astype(np.uint64) + np.uint64(salt)) * np.uint64(0xC2B2AE3D27D4EB4F))
+    h ^= h >> np.uint64(29)
+    h *= np.uint64(0xBF58476D1CE4E5B9)
+    h ^= h >> np.uint64(32)
+    h *= np.uint64(0x94D049BB133111EB)
+    h ^= h >> np.uint64(29)
+    return (h >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+def synth_cloud(n, ex, ey, seed=0, x0=0.0, y0=0.0, dtype=np.float32):
+    """terrain + one flat-roof building per 120 m lattice cell + vegetation
+    patches + 1e-4 low outliers; x, y, z rounded to `dtype` (float32 by default so
+    that a float4 stream and the float64 reference see identical numbers).
+    Returns x, y, z (float64 arrays holding dtype-representable values) and the
+    generator's own object label (1 = building/vegetation/outlier)."""
+    rng = np.random.default_rng(seed)
+    x = rng.random(n) * ex + x0
+    y = rng.random(n) * ey + y0
+    z = terrain(x, y) + rng.normal(0.0, 0.03, n)
+    with np.errstate(over='ignore'):
+        ix = np.floor(x / 120.0).astype(np.int64)
+        iy = np.floor(y / 120.0).astype(np.int64)
+        bx0 = ix * 120.0 + 10.0 + 50.0 * _lattice_rand(ix, iy, 1)
+        by0 = iy * 120.0 + 10.0 + 50.0 * _lattice_rand(ix, iy, 2)
+        bw = 8.0 + 52.0 * _lattice_rand(ix, iy, 3)
+        bd = 8.0 + 52.0 * _lattice_rand(ix, iy, 4)
+        bh = 3.0 + 27.0 * _lattice_rand(ix, iy, 5)
+    inb = (x >= bx0) & (x < bx0 + bw) & (y >= by0) & (y < by0 + bd)
+    roof = terrain(bx0 + .5 * bw, by0 + .5 * bd) + bh
+    z = np.where(inb, roof, z)
+    tp = 2.0 * np.pi
+    veg = (np.sin(tp * x / 310.0 + 1.0) * np.sin(tp * y / 270.0 + 2.0) > 0.35) & ~inb
+    lifted = veg & (rng.random(n) < 0.6)
+    z = z + np.where(lifted, 0.3 + 24.7 * rng.random(n), 0.0)
+    low = rng.random(n) < 1e-4
+    z = z - np.where(low, 5.0 + 45.0 * rng.random(n), 0.0)
+    label = (inb | lifted | low).astype(np.uint8)
+    x = x.astype(dtype).astype(np.float64)
+    y = y.astype(dtype).astype(np.float64)
+    z = z.astype(dtype).astype(np.float64)
+    return x, y, z, label
+
+
+def synth_dem(ny, nx, seed=3, nan_frac=0.3, dtype=np.float32):
+    """config 3: terrain + buildings sampled on a unit lattice as `dtype`, with
+    `nan_frac` of the cells set NaN."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.arange(ny, dtype=np.float64), np.arange(nx, dtype=np.float64), indexing='ij')
+    z = terrain(xx, yy)
+    with np.errstate(over='ignore'):
+        ix = np.floor(xx / 120.0).astype(np.int64)
+        iy = np.floor(yy / 120.0).astype(np.int64)
+        bx0 = ix * 120.0 + 10.0 + 50.0 * _lattice_rand(ix, iy, 1)
+        by0 = iy * 120.0 + 10.0 + 50.0 * _lattice_rand(ix, iy, 2)
+        bw = 8.0 + 52.0 * _lattice_rand(ix, iy, 3)
+        bd = 8.0 + 52.0 * _lattice_rand(ix, iy, 4)
+        bh = 3.0 + 27.0 * _lattice_rand(ix, iy, 5)
+    inb = (xx >= bx0) & (xx < bx0 + bw) & (yy >= by0) & (yy < by0 + bd)
+    z = np.where(inb, terrain(bx0 + .5 * bw, by0 + .5 * bd) + bh, z)
+    z = z + rng.normal(0.0, 0.03, z.shape)
+    z = z.astype(dtype)
+    if nan_frac > 0:
+        z[rng.random(z.shape) < nan_frac] = np.nan
+    return z
