@@ -52,6 +52,8 @@ extern "C" {
 
 int smrf_abi_version(void);
 const char* smrf_last_error(void);
+/* number of CUDA kernels this process has launched through the library (bench: gpu_launches) */
+unsigned long long smrf_launch_count(void);
 /* name of the opening implementation a call with these parameters would use
  * ("march_f32_w<=18", "tile_generic", ...) -- for logs and the bench JSON. */
 const char* smrf_open_variant(int dtype, int window);

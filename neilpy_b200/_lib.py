@@ -24,6 +24,7 @@ _ip = C.POINTER(C.c_int32)
 SIGNATURES = {
     'smrf_abi_version': (_i32, []),
     'smrf_last_error': (C.c_char_p, []),
+    'smrf_launch_count': (C.c_ulonglong, []),
     'smrf_open_variant': (C.c_char_p, [_i32, _i32]),
     'smrf_extent': (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     'smrf_bin_init': (_i32, [_vp, _i64, _i64, _i32, _i32, _vp]),

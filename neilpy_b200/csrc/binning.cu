@@ -6,6 +6,8 @@
 // decodes them in place, so there is no second grid-sized buffer.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace smrf {
@@ -17,6 +19,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------ extent
 __global__ void extent_init_kernel(long long* keys4, int64_t* nonfinite) {
@@ -169,12 +174,14 @@ static int bin_accumulate_t(const void* x, const void* y, const void* z, int64_t
             return SMRF_E_ARG;
     }
     SMRF_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 
 extern "C" {
 
 int smrf_abi_version(void) { return 1; }
+unsigned long long smrf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* smrf_last_error(void) { return g_err; }
 
 int smrf_extent(const void* x, const void* y, int64_t n, int point_fmt, double* out4, int64_t* nonfinite,
@@ -203,6 +210,7 @@ int smrf_extent(const void* x, const void* y, int64_t n, int point_fmt, double* 
     }
     extent_final_kernel<<<1, 32, 0, st>>>(keys, out4);
     SMRF_LAUNCH_CHECK();
+    count_launches(n > 0 ? 3 : 2);
     return 0;
 }
 
@@ -217,6 +225,7 @@ int smrf_bin_init(void* grid, int64_t ny, int64_t nx, int dtype, int bin_type, v
     else if (dtype == SMRF_F64) bin_init_kernel<double><<<g, 256, 0, st>>>((long long*)grid, n, bin_type);
     else SMRF_CHECK_ARG(false, "bad dtype");
     SMRF_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 
@@ -245,6 +254,7 @@ int smrf_bin_finalize(void* grid, uint8_t* empty, int64_t ny, int64_t nx, int dt
     else if (dtype == SMRF_F64) bin_finalize_kernel<double><<<g, 256, 0, st>>>((double*)grid, empty, n, bin_type);
     else SMRF_CHECK_ARG(false, "bad dtype");
     SMRF_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 

@@ -14,6 +14,7 @@
 namespace smrf {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // kernels launched by this process (smrf_launch_count)
 
 #define SMRF_CHECK_ARG(cond, msg)                              \
     do {                                                       \

@@ -62,6 +62,7 @@ int smrf_merge_punch(void* grid, const uint8_t* empty, const uint8_t* low, const
     else if (dtype == SMRF_F64) merge_punch_kernel<double><<<g, 256, 0, st>>>((double*)grid, empty, low, obj, object_cells, n);
     else SMRF_CHECK_ARG(false, "bad dtype");
     SMRF_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 
@@ -74,6 +75,7 @@ int smrf_slope(const void* grid, void* slope, int64_t ny, int64_t nx, int dtype,
     else if (dtype == SMRF_F64) slope_kernel<double><<<g, 256, 0, st>>>((const double*)grid, (double*)slope, ny, nx, cellsize);
     else SMRF_CHECK_ARG(false, "bad dtype");
     SMRF_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 

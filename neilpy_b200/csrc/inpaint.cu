@@ -252,6 +252,7 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
     if (dtype == SMRF_F32) scan_kernel<float><<<g1, kBlock, 0, st>>>((const float*)grid, w.unk, n, w.sc);
     else scan_kernel<double><<<g1, kBlock, 0, st>>>((const double*)grid, w.unk, n, w.sc);
     SMRF_LAUNCH_CHECK();
+    count_launches(1);
     unsigned long long counts[2];
     SMRF_CUDA(cudaMemcpyAsync(counts, &w.sc->n_known, sizeof(counts), cudaMemcpyDeviceToHost, st));
     SMRF_CUDA(cudaStreamSynchronize(st));
@@ -264,6 +265,7 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
         else init_u_kernel<double><<<g1, kBlock, 0, st>>>((const double*)grid, w.unk, w.u, n, w.sc);
         residual0_kernel<<<g2, kBlock, 0, st>>>(w, ny, nx);
         SMRF_LAUNCH_CHECK();
+        count_launches(2);
         unsigned long long bits = 0;
         SMRF_CUDA(cudaMemcpyAsync(&bits, &w.sc->rmax[0], 8, cudaMemcpyDeviceToHost, st));
         SMRF_CUDA(cudaStreamSynchronize(st));
@@ -277,6 +279,7 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
                 update_kernel<<<g2, kBlock, 0, st>>>(w, ny, nx, it);
             }
             SMRF_LAUNCH_CHECK();
+            count_launches(3 * burst);
             SMRF_CUDA(cudaMemcpyAsync(&bits, &w.sc->rmax[it], 8, cudaMemcpyDeviceToHost, st));
             SMRF_CUDA(cudaStreamSynchronize(st));
             memcpy(&rmax, &bits, 8);
@@ -285,6 +288,7 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
         if (dtype == SMRF_F32) writeback_kernel<float><<<g1, kBlock, 0, st>>>((float*)grid, w.unk, w.u, n);
         else writeback_kernel<double><<<g1, kBlock, 0, st>>>((double*)grid, w.unk, w.u, n);
         SMRF_LAUNCH_CHECK();
+        count_launches(1);
         SMRF_CUDA(cudaStreamSynchronize(st));
     }
     if (info_host) {

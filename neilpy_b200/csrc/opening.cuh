@@ -6,7 +6,7 @@ namespace smrf {
 
 // largest disk radius the register-marching kernels are instantiated for
 #ifndef SMRF_MARCH_MAX_W
-#define SMRF_MARCH_MAX_W 18
+#define SMRF_MARCH_MAX_W 40
 #endif
 
 bool open_march_available(int dtype, int window, int negate);

@@ -94,6 +94,7 @@ int open_window_generic(const void* in, void* out, void* tmp, uint8_t* mask, uin
         if (mask) threshold_kernel<double><<<gt, 256, 0, st>>>((const double*)in, (const double*)out, mask, when, nx, thr, widx, negate, row_lo, row_hi);
     }
     SMRF_LAUNCH_CHECK();
+    count_launches(mask ? 3 : 2);
     return 0;
 }
 

@@ -13,9 +13,11 @@
 //                    grows the horizontal window one cell per side per step
 //                    (R_h = min3(R_{h-1}, Z[x-h], Z[x+h]), one FMNMX3 per column) and,
 //                    whenever h equals the chord of some dy, folds R_h into the
-//                    accumulator of output row (y - dy).  The 2W+1 live output rows
-//                    per column sit in registers; the row loop is unrolled 2W+1 times
-//                    so that the rotating accumulator index is static.
+//                    accumulator of output row (y - dy).  The 2W+U live output rows
+//                    per column sit in registers; rows are processed in groups of U
+//                    (unrolled, so accumulator indices are static) and the accumulator
+//                    file is shifted by U registers after each group, which keeps the
+//                    loop body small enough to live in the instruction cache.
 //                    Finished erosion rows go to the shared ring Es (identity -inf
 //                    outside the image: the reference dilates an eroded image that does
 //                    not exist there).
@@ -41,19 +43,18 @@ constexpr int kThreads = 2 * kRoleThreads;
 
 template <int W>
 struct Cfg {
-    static constexpr int N = 2 * W + 1;
-    static constexpr int C = 4;
-    static constexpr int EW = kRoleThreads * C;                // erosion columns per CTA
-    static constexpr int NL = 2 * W + C;                       // elements a thread reads per row
-    static constexpr int NQ = (NL + 3) / 4;                    // ... as 16-byte quads
-    static constexpr int COLS = (kRoleThreads - 1) * C + NQ * 4;  // ring row length (floats)
-    static constexpr int XO = ((EW - 2 * W) / 4) * 4;          // output columns per CTA
-    static constexpr int RB = W <= 6 ? 8 : 4;                  // rows per hand-over batch
-    static constexpr int NB = 3;                               // batches in the Es ring
-    static constexpr int ZRING = 2 * RB;                       // Zs: double buffer
-    static constexpr int ERING = NB * RB;
+    static constexpr int C = W <= 20 ? 4 : 2;                   // adjacent columns per thread
+    static constexpr int U = W <= 4 ? 8 : 4;                    // rows per group (= hand-over batch)
+    static constexpr int A = 2 * W + U;                         // live accumulators per column
+    static constexpr int EW = kRoleThreads * C;                 // first-pass columns per CTA
+    static constexpr int NL = 2 * W + C;                        // elements a thread reads per row
+    static constexpr int NQ = (NL + C - 1) / C;                 // ... as C-wide vectors
+    static constexpr int COLS = ((kRoleThreads - 1) * C + NQ * C + 3) / 4 * 4;   // ring row length (floats)
+    static constexpr int XO = ((EW - 2 * W) / 4) * 4;           // output columns per CTA
+    static constexpr int I0 = (2 * W + U - 1) / U * U;          // warm-up rows per pass, whole groups
+    static constexpr int NB = 3;                                // batches in the Es ring
     static constexpr int MINB = W <= 2 ? 3 : (W <= 5 ? 2 : 1);  // CTAs per SM the register budget allows
-    static constexpr size_t kSmemBytes = (size_t)(ZRING + ERING) * COLS * sizeof(float) + 2 * NB * sizeof(uint64_t);
+    static constexpr size_t kSmemBytes = (size_t)(2 + NB) * U * COLS * sizeof(float) + 2 * NB * sizeof(uint64_t);
 
     __host__ __device__ static constexpr int isqrt(int v) {
         int h = 0;
@@ -109,7 +110,7 @@ __device__ __forceinline__ void cp_async(float* dst, const float* src) {
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void role_barrier() {   // the 128 E threads only (barrier 0 is __syncthreads)
+__device__ __forceinline__ void role_barrier() {   // the 128 first-pass threads only (barrier 0 is __syncthreads)
     asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
@@ -125,105 +126,109 @@ __device__ __forceinline__ float op3(float a, float b, float c) {
     return r;
 }
 
-// One incoming ring row for one thread: updates the 2W+1 rotating accumulators of its C
-// columns and returns in `fin` the output row that this row completes (local row i - W).
-// J = i mod (2W+1) is static.  srow points at the thread's first element: local index
-// W + c is the centre of column c.
-template <int W, bool IS_MAX, int J>
-__device__ __forceinline__ void chord_step(const float* __restrict__ srow, float (&acc)[2 * W + 1][4], float (&fin)[4]) {
-    using K = Cfg<W>;
-    constexpr int N = K::N;
-    float z[K::NQ * 4];
-    const float4* q = reinterpret_cast<const float4*>(srow);
-#pragma unroll
-    for (int i = 0; i < K::NQ; ++i) {
-        float4 v = q[i];
-        z[4 * i + 0] = v.x; z[4 * i + 1] = v.y; z[4 * i + 2] = v.z; z[4 * i + 3] = v.w;
+template <int C>
+__device__ __forceinline__ void load_vec(const float* p, float* dst) {
+    if constexpr (C == 4) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    } else if constexpr (C == 2) {
+        float2 v = *reinterpret_cast<const float2*>(p);
+        dst[0] = v.x; dst[1] = v.y;
+    } else {
+        dst[0] = *p;
     }
-    float R[4];
+}
+template <int C>
+__device__ __forceinline__ void store_vec(float* p, const float* src) {
+    if constexpr (C == 4) *reinterpret_cast<float4*>(p) = make_float4(src[0], src[1], src[2], src[3]);
+    else if constexpr (C == 2) *reinterpret_cast<float2*>(p) = make_float2(src[0], src[1]);
+    else *p = src[0];
+}
+
+// One incoming ring row (row u of the current group) for one thread.  acc[a] is the
+// accumulator of the output row (group base - W + a); this row contributes the chord of
+// dy to acc[u - dy + W]: its first term to acc[u + 2W] (dy = -W, assigned) and the last
+// term of acc[u] (dy = +W), which is returned in `fin`.  srow points at the thread's first
+// element: local index W + c is the centre of column c.
+template <int W, bool IS_MAX, int u>
+__device__ __forceinline__ void chord_step(const float* __restrict__ srow, float (&acc)[Cfg<W>::A][Cfg<W>::C],
+                                           float (&fin)[Cfg<W>::C]) {
+    using K = Cfg<W>;
+    constexpr int C = K::C;
+    float z[K::NQ * C];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) R[c] = z[W + c];
-    {   // chord of dy = +-W has half-length 0: the oldest output gets its last term, the newest its first
-        constexpr int s_old = (J + N - W) % N;
-        constexpr int s_new = (J + W) % N;
+    for (int i = 0; i < K::NQ; ++i) load_vec<C>(srow + i * C, z + i * C);
+    float R[C];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            fin[c] = op2<IS_MAX>(acc[s_old][c], R[c]);
-            acc[s_new][c] = R[c];
-        }
+    for (int c = 0; c < C; ++c) {
+        R[c] = z[W + c];
+        fin[c] = op2<IS_MAX>(acc[u][c], R[c]);     // chord of dy = +W has half-length 0
+        acc[u + 2 * W][c] = R[c];                  // ... and so has dy = -W: the newest output row
     }
     static_for<1, W + 1>([&](auto H) {
         constexpr int h = decltype(H)::value;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) R[c] = op3<IS_MAX>(R[c], z[W + c - h], z[W + c + h]);
+        for (int c = 0; c < C; ++c) R[c] = op3<IS_MAX>(R[c], z[W + c - h], z[W + c + h]);
         static_for<0, W>([&](auto DY) {
             constexpr int dy = decltype(DY)::value;
             if constexpr (K::half(dy) == h) {
-                if constexpr (dy == 0) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) acc[J][c] = op2<IS_MAX>(acc[J][c], R[c]);
-                } else {
-                    constexpr int s1 = (J + N - dy) % N;
-                    constexpr int s2 = (J + dy) % N;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        acc[s1][c] = op2<IS_MAX>(acc[s1][c], R[c]);
-                        acc[s2][c] = op2<IS_MAX>(acc[s2][c], R[c]);
-                    }
+                for (int c = 0; c < C; ++c) {
+                    acc[u + W - dy][c] = op2<IS_MAX>(acc[u + W - dy][c], R[c]);
+                    if constexpr (dy != 0) acc[u + W + dy][c] = op2<IS_MAX>(acc[u + W + dy][c], R[c]);
                 }
             }
         });
     });
 }
 
-// E threads: issue the copies of batch `b` of `last` rows [zr0 + b*RB, +RB) into its Zs slot.
-// VL floats per copy (16/8/4 bytes); anything outside the image is written as `ident`.
+// The first-pass warps stream group `g` of `last` rows [zr0 + g*U, +U) into its Zs slot:
+// warp wi copies rows wi, wi+4, ..; VL floats per cp.async (16 / 8 / 4 bytes); anything
+// outside the image is written as `ident`.
 template <int W, int VL>
-__device__ __forceinline__ void issue_batch(const Params& p, float* Zs, int b, int nZ, int64_t zc0, int64_t zr0,
-                                            float ident, int te) {
+__device__ __forceinline__ void issue_group(const Params& p, float* Zs, int g, int64_t zc0, int64_t zr0, float ident,
+                                            int wi, int lane) {
     using K = Cfg<W>;
-    constexpr int NCH = K::COLS / VL;   // chunks per row (COLS is a multiple of 4)
-    constexpr int TOT = NCH * K::RB;
-    float* slot = Zs + (size_t)(b & 1) * K::RB * K::COLS;
-#pragma unroll 2
-    for (int ch = te; ch < TOT; ch += kRoleThreads) {
-        const int rr = ch / NCH;
-        const int cc = ch - rr * NCH;
-        const int i = b * K::RB + rr;
-        const int64_t r = zr0 + i;
-        const int64_t g = zc0 + (int64_t)cc * VL;
-        float* dst = slot + (size_t)rr * K::COLS + cc * VL;
-        const bool rowok = i < nZ && r >= 0 && r < p.ny;
-        if (rowok && g >= 0 && g + VL <= p.nx) {
-            cp_async<4 * VL>(dst, p.in + r * p.nx + g);
-        } else {
+    constexpr int NCH = K::COLS / VL;
+    float* slot = Zs + (size_t)(g & 1) * K::U * K::COLS;
 #pragma unroll
-            for (int e = 0; e < VL; ++e) {
-                const bool ok = rowok && g + e >= 0 && g + e < p.nx;
-                dst[e] = ok ? __ldg(p.in + r * p.nx + g + e) : ident;
+    for (int rr0 = 0; rr0 < K::U; rr0 += 4) {
+        const int rr = rr0 + wi;
+        const int64_t r = zr0 + (int64_t)g * K::U + rr;
+        const bool rowok = r >= 0 && r < p.ny;
+        const float* src = p.in + r * p.nx + zc0;
+        float* dst = slot + (size_t)rr * K::COLS;
+        for (int cc = lane; cc < NCH; cc += 32) {
+            const int64_t g0 = zc0 + (int64_t)cc * VL;
+            if (rowok && g0 >= 0 && g0 + VL <= p.nx) {
+                cp_async<4 * VL>(dst + cc * VL, src + cc * VL);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VL; ++e)
+                    dst[cc * VL + e] = (rowok && g0 + e >= 0 && g0 + e < p.nx) ? __ldg(src + cc * VL + e) : ident;
             }
         }
     }
 }
 
 template <int W>
-__device__ __forceinline__ void issue_batch_any(const Params& p, float* Zs, int b, int nZ, int64_t zc0, int64_t zr0,
-                                                float ident, int te) {
-    if (p.vec_ok && (W % 2 == 0)) issue_batch<W, 4>(p, Zs, b, nZ, zc0, zr0, ident, te);
-    else if (p.vec_ok) issue_batch<W, 2>(p, Zs, b, nZ, zc0, zr0, ident, te);
-    else issue_batch<W, 1>(p, Zs, b, nZ, zc0, zr0, ident, te);
+__device__ __forceinline__ void issue_group_any(const Params& p, float* Zs, int g, int64_t zc0, int64_t zr0,
+                                                float ident, int wi, int lane) {
+    if (p.vec_ok && (W % 2 == 0)) issue_group<W, 4>(p, Zs, g, zc0, zr0, ident, wi, lane);
+    else if (p.vec_ok) issue_group<W, 2>(p, Zs, g, zc0, zr0, ident, wi, lane);
+    else issue_group<W, 1>(p, Zs, g, zc0, zr0, ident, wi, lane);
 }
 
 template <int W, bool NEG>
 __global__ void __launch_bounds__(kThreads, Cfg<W>::MINB) open_march_kernel(const Params p) {
     using K = Cfg<W>;
-    constexpr int N = K::N;
+    constexpr int C = K::C, U = K::U, A = K::A;
     constexpr bool E_MAX = NEG;        // erosion of -Z is -(dilation of Z)
     constexpr bool D_MAX = !NEG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* Zs = reinterpret_cast<float*>(smem_raw);
-    float* Es = Zs + (size_t)K::ZRING * K::COLS;
-    uint64_t* efull = reinterpret_cast<uint64_t*>(Es + (size_t)K::ERING * K::COLS);
+    float* Es = Zs + (size_t)2 * U * K::COLS;
+    uint64_t* efull = reinterpret_cast<uint64_t*>(Es + (size_t)K::NB * U * K::COLS);
     uint64_t* eempty = efull + K::NB;
 
     const int tid = threadIdx.x;
@@ -239,120 +244,136 @@ __global__ void __launch_bounds__(kThreads, Cfg<W>::MINB) open_march_kernel(cons
     const int64_t y0 = p.row_lo + (int64_t)blockIdx.y * p.seg;
     const int64_t y1 = (y0 + p.seg < p.row_hi) ? y0 + p.seg : p.row_hi;
     const int nOut = (int)(y1 - y0);
-    const int nZ = nOut + 4 * W;   // rows of `last` consumed: [y0 - 2W, y1 + 2W)
-    const int nE = nOut + 2 * W;   // erosion rows produced:  [y0 - W, y1 + W)
+    // Both passes emit from their group I0/U on, so that the first second-pass output is row
+    // y0: the second pass consumes first-pass rows from e0 = y0 + W - I0, and the first pass
+    // consumes rows of `last` from zr0 = e0 + W - I0.
+    const int nDg = (nOut + U - 1) / U;          // emitting groups of the second pass
+    const int nEg = nDg + K::I0 / U;             // emitting groups of the first pass = groups the second consumes
+    const int nZg = nEg + K::I0 / U;             // groups the first pass consumes
+    const int64_t e0 = y0 + W - K::I0;
+    const int64_t zr0 = e0 + W - K::I0;
     const float e_ident = E_MAX ? -INFINITY : INFINITY;   // "no sample" for the first pass
     const float d_ident = D_MAX ? -INFINITY : INFINITY;   // ... and for the second
 
     if (tid < kRoleThreads) {
         // ------------------------------------------------------------- first pass (erosion)
-        const int te = tid;
-        const int64_t zc0 = x0 - 2 * W, zr0 = y0 - 2 * W;
-        issue_batch_any<W>(p, Zs, 0, nZ, zc0, zr0, e_ident, te);
-        float acc[N][4];
+        const int te = tid, wi = tid >> 5, lane = tid & 31;
+        const int64_t zc0 = x0 - 2 * W;
+        issue_group_any<W>(p, Zs, 0, zc0, zr0, e_ident, wi, lane);
+        float acc[A][C];
 #pragma unroll
-        for (int s = 0; s < N; ++s)
+        for (int s = 0; s < A; ++s)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[s][c] = e_ident;
-        const int64_t ecol0 = x0 - W + 4 * te;
-        bool colok[4];
+            for (int c = 0; c < C; ++c) acc[s][c] = e_ident;
+        const int64_t ecol0 = x0 - W + C * te;
+        bool colok[C];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) colok[c] = (ecol0 + c >= 0) && (ecol0 + c < p.nx);
+        for (int c = 0; c < C; ++c) colok[c] = (ecol0 + c >= 0) && (ecol0 + c < p.nx);
         cp_async_wait_all();
         role_barrier();
-        for (int ib = 0; ib < nZ; ib += N) {
-            static_for<0, N>([&](auto JJ) {
-                constexpr int J = decltype(JJ)::value;
-                const int i = ib + J;
-                if (i < nZ) {
-                    const int b = i / K::RB;
-                    // batch b+1 streams in while batch b is consumed; its slot was last read in
-                    // batch b-1, which every E thread left through the barrier below
-                    if ((i % K::RB) == 0 && (b + 1) * K::RB < nZ) issue_batch_any<W>(p, Zs, b + 1, nZ, zc0, zr0, e_ident, te);
-                    float fin[4];
-                    chord_step<W, E_MAX, J>(Zs + (size_t)(i % K::ZRING) * K::COLS + 4 * te, acc, fin);
-                    if (i >= 2 * W) {
-                        const int k = i - 2 * W;
-                        const int kb = k / K::RB;
-                        if ((k % K::RB) == 0) mbar_wait(&eempty[kb % K::NB], ((kb / K::NB) & 1) ^ 1);
-                        const int64_t e = y0 - W + k;
-                        const bool rowok = e >= 0 && e < p.ny;
-                        float4 v;
-                        v.x = (rowok && colok[0]) ? fin[0] : d_ident;
-                        v.y = (rowok && colok[1]) ? fin[1] : d_ident;
-                        v.z = (rowok && colok[2]) ? fin[2] : d_ident;
-                        v.w = (rowok && colok[3]) ? fin[3] : d_ident;
-                        *reinterpret_cast<float4*>(Es + (size_t)(k % K::ERING) * K::COLS + 4 * te) = v;
-                        if ((k % K::RB) == K::RB - 1 || k == nE - 1) mbar_arrive(&efull[kb % K::NB]);
-                    }
-                    if ((i % K::RB) == K::RB - 1) {
-                        cp_async_wait_all();
-                        role_barrier();
-                    }
+        int slot = 0;
+        uint32_t phase = 0;
+#pragma unroll 1
+        for (int g = 0; g < nZg; ++g) {
+            // group g+1 streams in while group g is consumed; its slot was last read in group
+            // g-1, which every first-pass thread left through the barrier below
+            if (g + 1 < nZg) issue_group_any<W>(p, Zs, g + 1, zc0, zr0, e_ident, wi, lane);
+            const float* zb = Zs + (size_t)(g & 1) * U * K::COLS + C * te;
+            const int kg = g - K::I0 / U;
+            const bool emit = kg >= 0;
+            if (emit) mbar_wait(&eempty[slot], phase ^ 1);
+            float* eb = Es + (size_t)slot * U * K::COLS + C * te;
+            static_for<0, U>([&](auto UU) {
+                constexpr int u = decltype(UU)::value;
+                float fin[C];
+                chord_step<W, E_MAX, u>(zb + u * K::COLS, acc, fin);
+                if (emit) {
+                    const int64_t e = e0 + (int64_t)kg * U + u;
+                    const bool rowok = e >= 0 && e < p.ny;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) fin[c] = (rowok && colok[c]) ? fin[c] : d_ident;
+                    store_vec<C>(eb + u * K::COLS, fin);
                 }
             });
+            if (emit) {
+                mbar_arrive(&efull[slot]);
+                if (++slot == K::NB) { slot = 0; phase ^= 1; }
+            }
+#pragma unroll
+            for (int s = 0; s < 2 * W; ++s)
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[s][c] = acc[s + U][c];
+            cp_async_wait_all();
+            role_barrier();
         }
     } else {
         // ------------------------------------------------------------- second pass + threshold
         const int td = tid - kRoleThreads;
-        float acc[N][4];
+        float acc[A][C];
 #pragma unroll
-        for (int s = 0; s < N; ++s)
+        for (int s = 0; s < A; ++s)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[s][c] = d_ident;
-        const int64_t gx = x0 + 4 * td;
-        const bool dvalid = (td < K::XO / 4) && (gx < p.nx);
-        const bool vec = p.vec_ok && (gx + 3 < p.nx);
-        for (int ib = 0; ib < nE; ib += N) {
-            static_for<0, N>([&](auto JJ) {
-                constexpr int J = decltype(JJ)::value;
-                const int k = ib + J;
-                if (k < nE) {
-                    const int b = k / K::RB;
-                    if ((k % K::RB) == 0) mbar_wait(&efull[b % K::NB], (b / K::NB) & 1);
-                    const bool emit = dvalid && (k >= 2 * W);
-                    const int64_t off = (y0 + (k - 2 * W)) * p.nx + gx;
-                    float l[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (emit) {   // issue the re-read of `last` before the compute so L2 latency hides under it
-                        if (vec) {
-                            float4 t = __ldg(reinterpret_cast<const float4*>(p.in + off));
-                            l[0] = t.x; l[1] = t.y; l[2] = t.z; l[3] = t.w;
-                        } else {
+            for (int c = 0; c < C; ++c) acc[s][c] = d_ident;
+        const int64_t gx = x0 + C * td;
+        const bool dvalid = (td < K::XO / C) && (gx < p.nx);
+        const bool vec = p.vec_ok && (gx + C - 1 < p.nx);
+        int slot = 0;
+        uint32_t phase = 0;
+#pragma unroll 1
+        for (int g = 0; g < nEg; ++g) {
+            mbar_wait(&efull[slot], phase);
+            const float* eb = Es + (size_t)slot * U * K::COLS + C * td;
+            const int dg = g - K::I0 / U;
+            static_for<0, U>([&](auto UU) {
+                constexpr int u = decltype(UU)::value;
+                const int64_t d = y0 + (int64_t)dg * U + u;
+                const bool emit = dvalid && dg >= 0 && d < y1;
+                const int64_t off = d * p.nx + gx;
+                float l[C];
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (gx + c < p.nx) l[c] = __ldg(p.in + off + c);
+                for (int c = 0; c < C; ++c) l[c] = 0.f;
+                if (emit) {   // issue the re-read of `last` before the compute so L2 latency hides under it
+                    if (vec) load_vec<C>(p.in + off, l);
+                    else {
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+                            if (gx + c < p.nx) l[c] = __ldg(p.in + off + c);
+                    }
+                }
+                float fin[C];
+                chord_step<W, D_MAX, u>(eb + u * K::COLS, acc, fin);
+                if (emit) {
+                    if (p.out) {
+                        float o[C];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) o[c] = NEG ? -fin[c] : fin[c];
+                        if (vec) store_vec<C>(p.out + off, o);
+                        else {
+#pragma unroll
+                            for (int c = 0; c < C; ++c)
+                                if (gx + c < p.nx) p.out[off + c] = o[c];
                         }
                     }
-                    float fin[4];
-                    chord_step<W, D_MAX, J>(Es + (size_t)(k % K::ERING) * K::COLS + 4 * td, acc, fin);
-                    if ((k % K::RB) == K::RB - 1 || k == nE - 1) mbar_arrive(&eempty[b % K::NB]);
-                    if (emit) {
-                        if (p.out) {
-                            float o[4];
+                    if (p.mask) {
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) o[c] = NEG ? -fin[c] : fin[c];
-                            if (vec) *reinterpret_cast<float4*>(p.out + off) = make_float4(o[0], o[1], o[2], o[3]);
-                            else {
-#pragma unroll
-                                for (int c = 0; c < 4; ++c)
-                                    if (gx + c < p.nx) p.out[off + c] = o[c];
-                            }
-                        }
-                        if (p.mask) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                // (-Z) - open(-Z) == close(Z) - Z exactly
-                                const double d = NEG ? __dsub_rn((double)fin[c], (double)l[c])
-                                                     : __dsub_rn((double)l[c], (double)fin[c]);
-                                if ((gx + c < p.nx) && (d > p.thr)) {
-                                    p.mask[off + c] = 1;
-                                    if (p.when) p.when[off + c] = (uint8_t)p.widx;
-                                }
+                        for (int c = 0; c < C; ++c) {
+                            // (-Z) - open(-Z) == close(Z) - Z exactly
+                            const double df = NEG ? __dsub_rn((double)fin[c], (double)l[c])
+                                                  : __dsub_rn((double)l[c], (double)fin[c]);
+                            if ((gx + c < p.nx) && (df > p.thr)) {
+                                p.mask[off + c] = 1;
+                                if (p.when) p.when[off + c] = (uint8_t)p.widx;
                             }
                         }
                     }
                 }
             });
+            mbar_arrive(&eempty[slot]);
+            if (++slot == K::NB) { slot = 0; phase ^= 1; }
+#pragma unroll
+            for (int s = 0; s < 2 * W; ++s)
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[s][c] = acc[s + U][c];
         }
     }
 }
@@ -371,10 +392,10 @@ int launch_open_march_f32(const float* in, float* out, uint8_t* mask, uint8_t* w
     }
     const int64_t rows = row_hi - row_lo;
     const int nstrips = (int)((nx + K::XO - 1) / K::XO);
-    // Segment the rows so that (waves of CTAs) x (rows marched per CTA, incl. the 4W warm-up rows)
+    // Segment the rows so that (waves of CTAs) x (rows marched per CTA, incl. the 2*I0 warm-up rows)
     // is smallest: few long segments waste SMs, many short ones waste warm-up.
     const int64_t slots = (int64_t)num_sms() * K::MINB;
-    const int64_t min_seg = 4 * W < 32 ? 32 : 4 * W;
+    const int64_t min_seg = 2 * K::I0 < 32 ? 32 : 2 * K::I0;
     int64_t max_segs = rows / min_seg;
     if (max_segs < 1) max_segs = 1;
     if (max_segs > 4096) max_segs = 4096;
@@ -382,10 +403,11 @@ int launch_open_march_f32(const float* in, float* out, uint8_t* mask, uint8_t* w
     for (int64_t n = 1; n <= max_segs; ++n) {
         const int64_t ctas = n * nstrips;
         const int64_t waves = (ctas + slots - 1) / slots;
-        const int64_t cost = waves * ((rows + n - 1) / n + 4 * W);
+        const int64_t cost = waves * ((rows + n - 1) / n + 2 * K::I0);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_n = n; }
     }
-    const int seg = (int)((rows + best_n - 1) / best_n);
+    int seg = (int)((rows + best_n - 1) / best_n);
+    seg = (seg + K::U - 1) / K::U * K::U;
     const int nsegs = (int)((rows + seg - 1) / seg);
     march::Params p;
     p.in = in; p.out = out; p.mask = mask; p.when = when;
@@ -395,6 +417,7 @@ int launch_open_march_f32(const float* in, float* out, uint8_t* mask, uint8_t* w
     dim3 grid((unsigned)nstrips, (unsigned)nsegs);
     march::open_march_kernel<W, NEG><<<grid, march::kThreads, K::kSmemBytes, st>>>(p);
     SMRF_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 

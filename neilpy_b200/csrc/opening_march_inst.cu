@@ -67,4 +67,70 @@ SMRF_INST(17, false)
 #if SMRF_W_LO <= 18 && 18 <= SMRF_W_HI
 SMRF_INST(18, false)
 #endif
+#if SMRF_W_LO <= 19 && 19 <= SMRF_W_HI
+SMRF_INST(19, false)
+#endif
+#if SMRF_W_LO <= 20 && 20 <= SMRF_W_HI
+SMRF_INST(20, false)
+#endif
+#if SMRF_W_LO <= 21 && 21 <= SMRF_W_HI
+SMRF_INST(21, false)
+#endif
+#if SMRF_W_LO <= 22 && 22 <= SMRF_W_HI
+SMRF_INST(22, false)
+#endif
+#if SMRF_W_LO <= 23 && 23 <= SMRF_W_HI
+SMRF_INST(23, false)
+#endif
+#if SMRF_W_LO <= 24 && 24 <= SMRF_W_HI
+SMRF_INST(24, false)
+#endif
+#if SMRF_W_LO <= 25 && 25 <= SMRF_W_HI
+SMRF_INST(25, false)
+#endif
+#if SMRF_W_LO <= 26 && 26 <= SMRF_W_HI
+SMRF_INST(26, false)
+#endif
+#if SMRF_W_LO <= 27 && 27 <= SMRF_W_HI
+SMRF_INST(27, false)
+#endif
+#if SMRF_W_LO <= 28 && 28 <= SMRF_W_HI
+SMRF_INST(28, false)
+#endif
+#if SMRF_W_LO <= 29 && 29 <= SMRF_W_HI
+SMRF_INST(29, false)
+#endif
+#if SMRF_W_LO <= 30 && 30 <= SMRF_W_HI
+SMRF_INST(30, false)
+#endif
+#if SMRF_W_LO <= 31 && 31 <= SMRF_W_HI
+SMRF_INST(31, false)
+#endif
+#if SMRF_W_LO <= 32 && 32 <= SMRF_W_HI
+SMRF_INST(32, false)
+#endif
+#if SMRF_W_LO <= 33 && 33 <= SMRF_W_HI
+SMRF_INST(33, false)
+#endif
+#if SMRF_W_LO <= 34 && 34 <= SMRF_W_HI
+SMRF_INST(34, false)
+#endif
+#if SMRF_W_LO <= 35 && 35 <= SMRF_W_HI
+SMRF_INST(35, false)
+#endif
+#if SMRF_W_LO <= 36 && 36 <= SMRF_W_HI
+SMRF_INST(36, false)
+#endif
+#if SMRF_W_LO <= 37 && 37 <= SMRF_W_HI
+SMRF_INST(37, false)
+#endif
+#if SMRF_W_LO <= 38 && 38 <= SMRF_W_HI
+SMRF_INST(38, false)
+#endif
+#if SMRF_W_LO <= 39 && 39 <= SMRF_W_HI
+SMRF_INST(39, false)
+#endif
+#if SMRF_W_LO <= 40 && 40 <= SMRF_W_HI
+SMRF_INST(40, false)
+#endif
 }  // namespace smrf

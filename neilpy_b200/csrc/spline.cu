@@ -246,6 +246,7 @@ int smrf_spline_prefilter(const void* grid, void* coef, int64_t ny, int64_t nx, 
         SMRF_CUDA(cudaMemcpyAsync(coef, s2, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
     }
     SMRF_LAUNCH_CHECK();
+    count_launches(dtype == SMRF_F32 ? 7 : 6);
     return 0;
 }
 
@@ -277,6 +278,7 @@ int smrf_classify(const void* x, const void* y, const void* z, int64_t n, int po
     }
 #undef SMRF_GO
     SMRF_LAUNCH_CHECK();
+    count_launches(1);
     return 0;
 }
 

@@ -105,7 +105,7 @@ def open_window(nb, Z, w, thr=0.0, negate=0, rows=None):
 
 
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])
-@pytest.mark.parametrize('w', [1, 2, 3, 4, 5, 6, 7, 8, 11, 13, 16, 17, 18, 19, 25])
+@pytest.mark.parametrize('w', [1, 2, 3, 4, 5, 6, 7, 8, 11, 13, 16, 17, 18, 19, 20, 21, 25, 33, 36, 40, 41])
 def test_single_opening_bit_exact(nb, dtype, w):
     # 1000 columns: two column strips of the marching kernel; 300 rows: several row segments
     Z = surface(300, 1000, w, dtype)
@@ -135,7 +135,7 @@ def test_opening_odd_shapes_against_the_border_rule(nb, shape, w):
 
 def test_march_and_direct_kernels_agree(nb, monkeypatch):
     Z = surface(257, 1203, 99, np.float32)
-    a = {w: open_window(nb, Z, w, thr=0.1 * w) for w in (1, 5, 12, 18)}
+    a = {w: open_window(nb, Z, w, thr=0.1 * w) for w in (1, 5, 12, 18, 23, 37)}
     monkeypatch.setenv('SMRF_OPEN_IMPL', 'generic')
     for w, (s, m) in a.items():
         s2, m2 = open_window(nb, Z, w, thr=0.1 * w)
@@ -218,7 +218,8 @@ def test_inpaint_edge_cases(nb):
     keep = B.copy()
     out = nb.inpaint_nans_by_springs(B)
     assert eq_nan(B, keep) and not np.isnan(out).any()                           # input not mutated
-    assert nb.inpaint_nans_by_springs(B, inplace=True) is None and np.array_equal(B, out)
+    # (dot products are reduced with atomics: two solves agree to rounding, not bit for bit)
+    assert nb.inpaint_nans_by_springs(B, inplace=True) is None and np.allclose(B, out, rtol=0, atol=1e-8)
     one = np.array([[1.0, np.nan, 3.0]])
     assert np.allclose(nb.inpaint_nans_by_springs(one), [[1.0, 2.0, 3.0]], atol=1e-9)
 
