@@ -4,14 +4,21 @@
 // LSQR for the least-squares displacement; the minimiser satisfies, for every NaN cell i,
 //     deg(i) u_i - sum_{NaN nbrs j} u_j = sum_{known nbrs k} a_k,   deg = in-grid neighbours,
 // a symmetric positive-definite system (per connected NaN region that touches a known
-// cell).  Here it is solved in float64 by preconditioned conjugate gradients whose every
-// vector lives in HBM; dot products are reduced on the device (block reduce + one
-// atomicAdd(double) per block) into per-iteration slots, so an iteration is three
-// stream-ordered kernel launches with no host round trip; the host only polls the
-// residual max-norm every kCheckEvery iterations.
-//
-// HBM-bound stencil kernels: every launch is a 2-D grid over (row, 256-column block);
-// neighbours come from L1/L2.
+// cell).  Here it is solved by conjugate gradients in float64 whose every vector lives in
+// HBM, preconditioned by one geometric multigrid V(2,2)-cycle per iteration:
+//   - cell-centred 2x2 coarsening; a coarse cell is unknown only if all its children are
+//     (the coarse domains shrink, so Dirichlet data never leaks into a correction);
+//   - damped-Jacobi smoothing, piecewise-constant prolongation and its transpose as the
+//     restriction, the 5-point operator rediscretised on every level: the cycle is a
+//     symmetric positive-definite operator, as CG needs;
+//   - the cycle runs in float32 (it only steers the search direction; the residual
+//     recurrence that decides convergence is float64).
+// Dot products are reduced on the device (block reduce + one atomicAdd(double) per block)
+// into per-iteration slots, so an iteration is a fixed sequence of stream-ordered launches
+// with no host round trip; the host polls the residual max-norm every kCheckEvery iterations.
+// Every kernel is an HBM-bound stencil pass over (row, 256-column) tiles; neighbours come
+// from L1/L2.  SMRF_INPAINT_PRECOND=jacobi switches the V-cycle off (diagnostics).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -20,8 +27,11 @@ namespace smrf {
 namespace inpaint {
 
 constexpr int kMaxIter = 1 << 15;
-constexpr int kCheckEvery = 16;
+constexpr int kCheckEvery = 8;
 constexpr int kBlock = 256;
+constexpr int kMaxLevels = 20;
+constexpr float kOmega = 0.8f;
+constexpr int kCoarsestSweeps = 8;
 
 struct Scalars {          // device-resident, indexed by iteration
     double rz[kMaxIter + 2];
@@ -32,26 +42,53 @@ struct Scalars {          // device-resident, indexed by iteration
     unsigned long long n_unknown;
 };
 
+struct Level {
+    int64_t ny, nx;
+    uint8_t* m;       // 1 = unknown on this level
+    float *x, *y, *b; // two iterates (ping-pong) and the right-hand side
+};
+
 struct Ws {
-    double *u, *r, *z, *p, *q;
-    uint8_t* unk;
+    double *u, *r, *p, *q;
     Scalars* sc;
+    int nlev;
+    Level lev[kMaxLevels];
 };
 
 static inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static Ws carve(void* workspace, int64_t n) {
+static int level_dims(int64_t ny, int64_t nx, int64_t* lny, int64_t* lnx) {
+    int n = 0;
+    while (n < kMaxLevels) {
+        lny[n] = ny; lnx[n] = nx; ++n;
+        if (ny <= 2 && nx <= 2) break;
+        ny = (ny + 1) / 2; nx = (nx + 1) / 2;
+    }
+    return n;
+}
+
+static size_t carve(void* workspace, int64_t ny, int64_t nx, Ws* w) {
     char* b = (char*)workspace;
-    Ws w;
-    size_t plane = align_up((size_t)n * 8);
-    w.u = (double*)b; b += plane;
-    w.r = (double*)b; b += plane;
-    w.z = (double*)b; b += plane;
-    w.p = (double*)b; b += plane;
-    w.q = (double*)b; b += plane;
-    w.unk = (uint8_t*)b; b += align_up((size_t)n);
-    w.sc = (Scalars*)b;
-    return w;
+    const size_t n = (size_t)ny * (size_t)nx;
+    const size_t plane = align_up(n * 8);
+    Ws t;
+    t.u = (double*)b; b += plane;
+    t.r = (double*)b; b += plane;
+    t.p = (double*)b; b += plane;
+    t.q = (double*)b; b += plane;
+    int64_t lny[kMaxLevels], lnx[kMaxLevels];
+    t.nlev = level_dims(ny, nx, lny, lnx);
+    for (int l = 0; l < t.nlev; ++l) {
+        const size_t nl = (size_t)lny[l] * (size_t)lnx[l];
+        t.lev[l].ny = lny[l]; t.lev[l].nx = lnx[l];
+        t.lev[l].m = (uint8_t*)b; b += align_up(nl);
+        t.lev[l].x = (float*)b; b += align_up(nl * 4);
+        t.lev[l].y = (float*)b; b += align_up(nl * 4);
+        t.lev[l].b = (float*)b; b += align_up(nl * 4);
+    }
+    t.sc = (Scalars*)b; b += align_up(sizeof(Scalars));
+    if (w) *w = t;
+    return (size_t)(b - (char*)workspace);
 }
 
 __device__ __forceinline__ double block_sum(double v) {
@@ -85,6 +122,27 @@ __device__ __forceinline__ double block_max(double v) {
     return t;
 }
 
+// Tiles of one row x 256 columns, walked with a block stride: a few thousand CTAs whatever
+// the grid size, so the per-block atomics of the reductions stay cheap.
+struct Tiles {
+    int64_t ny, nx, per_row, total;
+    __host__ __device__ Tiles(int64_t ny_, int64_t nx_)
+        : ny(ny_), nx(nx_), per_row((nx_ + kBlock - 1) / kBlock), total(ny_ * ((nx_ + kBlock - 1) / kBlock)) {}
+};
+// body sees: int64_t Y_, X_ (tile row, column of this thread); bool IN_ (X_ < nx)
+__device__ __forceinline__ int64_t tile_first() { return blockIdx.x; }
+__device__ __forceinline__ int64_t tile_step() { return gridDim.x; }
+__device__ __forceinline__ int64_t tile_lane() { return threadIdx.x; }
+#define SMRF_FOR_TILES(T, Y_, X_, IN_)                                                      \
+    for (int64_t t__ = tile_first(); t__ < (T).total; t__ += tile_step())                   \
+        if (const int64_t Y_ = t__ / (T).per_row; true)                                     \
+            if (const int64_t X_ = (t__ - Y_ * (T).per_row) * kBlock + tile_lane(); true)   \
+                if (const bool IN_ = X_ < (T).nx; true)
+
+__device__ __forceinline__ int degree(int64_t y, int64_t x, int64_t ny, int64_t nx) {
+    return (y > 0) + (y + 1 < ny) + (x > 0) + (x + 1 < nx);
+}
+
 // ---- pass 0: NaN mask, statistics of the known cells ------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kBlock) scan_kernel(const T* __restrict__ grid, uint8_t* __restrict__ unk, int64_t n,
@@ -116,19 +174,17 @@ __global__ void __launch_bounds__(kBlock) init_u_kernel(const T* __restrict__ gr
         u[i] = unk[i] ? mean : (double)grid[i];
 }
 
-__device__ __forceinline__ int degree(int64_t y, int64_t x, int64_t ny, int64_t nx) {
-    return (y > 0) + (y + 1 < ny) + (x > 0) + (x + 1 < nx);
-}
-
 // r = b - A u on the unknown cells (u holds the known values at known cells, so the
-// right-hand side is implicit); z = r / deg; rz[0] = r.z; rmax[0] = max |r|
+// right-hand side is implicit); b0 = (float) r feeds the preconditioner; rmax[0] = max |r|
 __global__ void __launch_bounds__(kBlock) residual0_kernel(Ws w, int64_t ny, int64_t nx) {
-    double rz = 0.0, rm = 0.0;
-    const int64_t x = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    for (int64_t y = blockIdx.y; y < ny; y += gridDim.y) {
-        if (x < nx) {
+    const Tiles T(ny, nx);
+    const uint8_t* unk = w.lev[0].m;
+    double rm = 0.0;
+    SMRF_FOR_TILES(T, y, x, in) {
+        if (in) {
             const int64_t i = y * nx + x;
-            if (w.unk[i]) {
+            float rf = 0.f;
+            if (unk[i]) {
                 double s = 0.0;
                 if (y > 0) s += w.u[i - nx];
                 if (y + 1 < ny) s += w.u[i + nx];
@@ -136,40 +192,70 @@ __global__ void __launch_bounds__(kBlock) residual0_kernel(Ws w, int64_t ny, int
                 if (x + 1 < nx) s += w.u[i + 1];
                 const int d = degree(y, x, ny, nx);
                 const double r = d ? s - (double)d * w.u[i] : 0.0;
-                const double z = d ? r / (double)d : 0.0;
-                w.r[i] = r; w.z[i] = z; w.p[i] = 0.0;
-                rz += r * z; rm = fmax(rm, fabs(r));
+                w.r[i] = r; w.p[i] = 0.0;
+                rf = (float)r;
+                rm = fmax(rm, fabs(r));
+            }
+            w.lev[0].b[i] = rf;
+        }
+    }
+    rm = block_max(rm);
+    if (threadIdx.x == 0) atomicMax(&w.sc->rmax[0], (unsigned long long)__double_as_longlong(rm));
+}
+
+// rz[k] = r.z, then p = z + beta p with beta = rz[k] / rz[k-1] needs the finished sum: two kernels.
+template <bool JACOBI>
+__global__ void __launch_bounds__(kBlock) rz_kernel(Ws w, const float* __restrict__ z, int64_t ny, int64_t nx, int k) {
+    const Tiles T(ny, nx);
+    const uint8_t* unk = w.lev[0].m;
+    double rz = 0.0;
+    SMRF_FOR_TILES(T, y, x, in) {
+        if (in) {
+            const int64_t i = y * nx + x;
+            if (unk[i]) {
+                const double r = w.r[i];
+                const int d = degree(y, x, ny, nx);
+                const double zi = JACOBI ? (d ? r / (double)d : 0.0) : (double)z[i];
+                rz += r * zi;
             }
         }
     }
     rz = block_sum(rz);
-    rm = block_max(rm);
-    if (threadIdx.x == 0) {
-        if (rz != 0.0) atomicAdd(&w.sc->rz[0], rz);
-        atomicMax(&w.sc->rmax[0], (unsigned long long)__double_as_longlong(rm));
+    if (threadIdx.x == 0 && rz != 0.0) atomicAdd(&w.sc->rz[k], rz);
+}
+
+template <bool JACOBI>
+__global__ void __launch_bounds__(kBlock) p_update_kernel(Ws w, const float* __restrict__ z, int64_t ny, int64_t nx,
+                                                          int k) {
+    const Tiles T(ny, nx);
+    const uint8_t* unk = w.lev[0].m;
+    const double beta = (k == 0 || w.sc->rz[k - 1] == 0.0) ? 0.0 : w.sc->rz[k] / w.sc->rz[k - 1];
+    SMRF_FOR_TILES(T, y, x, in) {
+        if (in) {
+            const int64_t i = y * nx + x;
+            if (unk[i]) {
+                const int d = degree(y, x, ny, nx);
+                const double zi = JACOBI ? (d ? w.r[i] / (double)d : 0.0) : (double)z[i];
+                w.p[i] = zi + beta * w.p[i];
+            }
+        }
     }
 }
 
-// p = z + beta p,  beta = rz[k] / rz[k-1]
-__global__ void __launch_bounds__(kBlock) p_update_kernel(Ws w, int64_t n, int k) {
-    const double beta = (k == 0 || w.sc->rz[k - 1] == 0.0) ? 0.0 : w.sc->rz[k] / w.sc->rz[k - 1];
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
-        if (w.unk[i]) w.p[i] = w.z[i] + beta * w.p[i];
-}
-
-// q = A p (p is zero on known cells by construction: never written there);  pq[k] = p.q
+// q = A p (p is only ever read on unknown cells);  pq[k] = p.q
 __global__ void __launch_bounds__(kBlock) apply_kernel(Ws w, int64_t ny, int64_t nx, int k) {
+    const Tiles T(ny, nx);
+    const uint8_t* unk = w.lev[0].m;
     double pq = 0.0;
-    const int64_t x = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    for (int64_t y = blockIdx.y; y < ny; y += gridDim.y) {
-        if (x < nx) {
+    SMRF_FOR_TILES(T, y, x, in) {
+        if (in) {
             const int64_t i = y * nx + x;
-            if (w.unk[i]) {
+            if (unk[i]) {
                 double s = 0.0;
-                if (y > 0 && w.unk[i - nx]) s += w.p[i - nx];
-                if (y + 1 < ny && w.unk[i + nx]) s += w.p[i + nx];
-                if (x > 0 && w.unk[i - 1]) s += w.p[i - 1];
-                if (x + 1 < nx && w.unk[i + 1]) s += w.p[i + 1];
+                if (y > 0 && unk[i - nx]) s += w.p[i - nx];
+                if (y + 1 < ny && unk[i + nx]) s += w.p[i + nx];
+                if (x > 0 && unk[i - 1]) s += w.p[i - 1];
+                if (x + 1 < nx && unk[i + 1]) s += w.p[i + 1];
                 const double pi = w.p[i];
                 const double q = (double)degree(y, x, ny, nx) * pi - s;
                 w.q[i] = q;
@@ -181,31 +267,27 @@ __global__ void __launch_bounds__(kBlock) apply_kernel(Ws w, int64_t ny, int64_t
     if (threadIdx.x == 0 && pq != 0.0) atomicAdd(&w.sc->pq[k], pq);
 }
 
-// u += alpha p; r -= alpha q; z = r / deg; rz[k+1] = r.z; rmax[k+1] = max |r|
+// u += alpha p; r -= alpha q; b0 = (float) r; rmax[k+1] = max |r|
 __global__ void __launch_bounds__(kBlock) update_kernel(Ws w, int64_t ny, int64_t nx, int k) {
+    const Tiles T(ny, nx);
+    const uint8_t* unk = w.lev[0].m;
     const double pqk = w.sc->pq[k];
     const double alpha = pqk != 0.0 ? w.sc->rz[k] / pqk : 0.0;
-    double rz = 0.0, rm = 0.0;
-    const int64_t x = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    for (int64_t y = blockIdx.y; y < ny; y += gridDim.y) {
-        if (x < nx) {
+    double rm = 0.0;
+    SMRF_FOR_TILES(T, y, x, in) {
+        if (in) {
             const int64_t i = y * nx + x;
-            if (w.unk[i]) {
+            if (unk[i]) {
                 w.u[i] += alpha * w.p[i];
                 const double r = w.r[i] - alpha * w.q[i];
-                const int d = degree(y, x, ny, nx);
-                const double z = d ? r / (double)d : 0.0;
-                w.r[i] = r; w.z[i] = z;
-                rz += r * z; rm = fmax(rm, fabs(r));
+                w.r[i] = r;
+                w.lev[0].b[i] = (float)r;
+                rm = fmax(rm, fabs(r));
             }
         }
     }
-    rz = block_sum(rz);
     rm = block_max(rm);
-    if (threadIdx.x == 0) {
-        if (rz != 0.0) atomicAdd(&w.sc->rz[k + 1], rz);
-        atomicMax(&w.sc->rmax[k + 1], (unsigned long long)__double_as_longlong(rm));
-    }
+    if (threadIdx.x == 0) atomicMax(&w.sc->rmax[k + 1], (unsigned long long)__double_as_longlong(rm));
 }
 
 template <typename T>
@@ -213,6 +295,149 @@ __global__ void __launch_bounds__(kBlock) writeback_kernel(T* __restrict__ grid,
                                                            const double* __restrict__ u, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
         if (unk[i]) grid[i] = (T)u[i];
+}
+
+// ---- multigrid pieces (float32) -------------------------------------------------------------
+// coarse cell unknown <=> every in-grid child unknown
+__global__ void __launch_bounds__(kBlock) coarsen_kernel(const uint8_t* __restrict__ mf, uint8_t* __restrict__ mc,
+                                                         int64_t fy, int64_t fx, int64_t cy, int64_t cx) {
+    const Tiles T(cy, cx);
+    SMRF_FOR_TILES(T, Y, X, in) {
+        if (in) {
+            uint8_t all = 1;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int64_t y = 2 * Y + a, x = 2 * X + b;
+                    if (y < fy && x < fx) all &= mf[y * fx + x];
+                }
+            mc[Y * cx + X] = all;
+        }
+    }
+}
+
+// One damped-Jacobi sweep  out = x + omega (b - A x) / deg  on unknown cells, 0 elsewhere
+// (iterates are kept at zero off the unknown set, so neighbours need no mask test).
+// FIRST: x is the zero vector.
+template <bool FIRST>
+__global__ void __launch_bounds__(kBlock) smooth_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                        const float* __restrict__ b, const uint8_t* __restrict__ m,
+                                                        int64_t ny, int64_t nx) {
+    const Tiles T(ny, nx);
+    SMRF_FOR_TILES(T, y, xx, in) {
+        if (in) {
+            const int64_t i = y * nx + xx;
+            float v = 0.f;
+            if (m[i]) {
+                const float d = (float)degree(y, xx, ny, nx);
+                if (FIRST) {
+                    v = d > 0.f ? kOmega * b[i] / d : 0.f;
+                } else {
+                    float s = 0.f;
+                    if (y > 0) s += x[i - nx];
+                    if (y + 1 < ny) s += x[i + nx];
+                    if (xx > 0) s += x[i - 1];
+                    if (xx + 1 < nx) s += x[i + 1];
+                    const float xi = x[i];
+                    v = d > 0.f ? xi + kOmega * (b[i] - (d * xi - s)) / d : 0.f;
+                }
+            }
+            out[i] = v;
+        }
+    }
+}
+
+// bc = P^T (b - A x): the sum of the residuals of the (up to four) children
+__global__ void __launch_bounds__(kBlock) restrict_kernel(const float* __restrict__ x, const float* __restrict__ b,
+                                                          const uint8_t* __restrict__ mc, float* __restrict__ bc,
+                                                          int64_t fy, int64_t fx, int64_t cy, int64_t cx) {
+    const Tiles T(cy, cx);
+    SMRF_FOR_TILES(T, Y, X, in) {
+        if (in) {
+            float acc = 0.f;
+            if (mc[Y * cx + X]) {      // all children unknown
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int64_t y = 2 * Y + a, xx = 2 * X + c;
+                        if (y < fy && xx < fx) {
+                            const int64_t i = y * fx + xx;
+                            float s = 0.f;
+                            if (y > 0) s += x[i - fx];
+                            if (y + 1 < fy) s += x[i + fx];
+                            if (xx > 0) s += x[i - 1];
+                            if (xx + 1 < fx) s += x[i + 1];
+                            acc += b[i] - ((float)degree(y, xx, fy, fx) * x[i] - s);
+                        }
+                    }
+            }
+            bc[Y * cx + X] = acc;
+        }
+    }
+}
+
+// x += P xc on the unknown fine cells
+__global__ void __launch_bounds__(kBlock) prolong_kernel(float* __restrict__ x, const float* __restrict__ xc,
+                                                         const uint8_t* __restrict__ m, int64_t fy, int64_t fx,
+                                                         int64_t cx) {
+    const Tiles T(fy, fx);
+    SMRF_FOR_TILES(T, y, xx, in) {
+        if (in) {
+            const int64_t i = y * fx + xx;
+            if (m[i]) x[i] += xc[(y >> 1) * cx + (xx >> 1)];
+        }
+    }
+}
+
+static inline int tile_grid(int64_t ny, int64_t nx) {
+    int64_t t = ny * ((nx + kBlock - 1) / kBlock);
+    int64_t cap = (int64_t)num_sms() * 16;
+    if (t > cap) t = cap;
+    if (t < 1) t = 1;
+    return (int)t;
+}
+
+// z = M^-1 b0: one V(2,2) cycle; returns the buffer holding the level-0 result
+static const float* vcycle(Ws& w, cudaStream_t st, int* launches) {
+    const int L = w.nlev;
+    float* cur[kMaxLevels];
+    int n = 0;
+    for (int l = 0; l < L; ++l) {
+        Level& v = w.lev[l];
+        const int g = tile_grid(v.ny, v.nx);
+        smooth_kernel<true><<<g, kBlock, 0, st>>>(nullptr, v.x, v.b, v.m, v.ny, v.nx);
+        ++n;
+        if (l == L - 1) {
+            float *a = v.x, *b = v.y;
+            for (int s = 1; s < kCoarsestSweeps; ++s) {
+                smooth_kernel<false><<<g, kBlock, 0, st>>>(a, b, v.b, v.m, v.ny, v.nx);
+                float* t = a; a = b; b = t;
+                ++n;
+            }
+            cur[l] = a;
+        } else {
+            smooth_kernel<false><<<g, kBlock, 0, st>>>(v.x, v.y, v.b, v.m, v.ny, v.nx);
+            cur[l] = v.y;
+            Level& c = w.lev[l + 1];
+            restrict_kernel<<<tile_grid(c.ny, c.nx), kBlock, 0, st>>>(cur[l], v.b, c.m, c.b, v.ny, v.nx, c.ny, c.nx);
+            n += 2;
+        }
+    }
+    for (int l = L - 2; l >= 0; --l) {
+        Level& v = w.lev[l];
+        const int g = tile_grid(v.ny, v.nx);
+        float* a = cur[l];
+        float* b = (a == v.x) ? v.y : v.x;
+        prolong_kernel<<<g, kBlock, 0, st>>>(a, cur[l + 1], v.m, v.ny, v.nx, w.lev[l + 1].nx);
+        smooth_kernel<false><<<g, kBlock, 0, st>>>(a, b, v.b, v.m, v.ny, v.nx);
+        smooth_kernel<false><<<g, kBlock, 0, st>>>(b, a, v.b, v.m, v.ny, v.nx);
+        cur[l] = a;
+        n += 3;
+    }
+    *launches += n;
+    return cur[0];
 }
 
 }  // namespace inpaint
@@ -224,8 +449,8 @@ using namespace smrf::inpaint;
 extern "C" {
 
 size_t smrf_inpaint_workspace_bytes(int64_t ny, int64_t nx) {
-    size_t n = (size_t)ny * (size_t)nx;
-    return 5 * align_up(n * 8) + align_up(n) + align_up(sizeof(Scalars));
+    if (ny <= 0 || nx <= 0) return 0;
+    return carve(nullptr, ny, nx, nullptr);
 }
 
 int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown, void* workspace,
@@ -239,58 +464,89 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
         return SMRF_E_WORKSPACE;
     }
     if (max_iter <= 0 || max_iter > kMaxIter) max_iter = kMaxIter;
+    const char* env = getenv("SMRF_INPAINT_PRECOND");
+    const bool jacobi = env && strcmp(env, "jacobi") == 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = ny * nx;
-    Ws w = carve(workspace, n);
+    Ws w;
+    carve(workspace, ny, nx, &w);
     SMRF_CUDA(cudaMemsetAsync(w.sc, 0, sizeof(Scalars), st));
 
     int g1 = (int)((n + kBlock - 1) / kBlock);
     int cap = num_sms() * 16;
     if (g1 > cap) g1 = cap;
-    dim3 g2((unsigned)((nx + kBlock - 1) / kBlock), (unsigned)(ny < 32768 ? ny : 32768));
+    const int g2 = tile_grid(ny, nx);
+    int launches = 0;
 
-    if (dtype == SMRF_F32) scan_kernel<float><<<g1, kBlock, 0, st>>>((const float*)grid, w.unk, n, w.sc);
-    else scan_kernel<double><<<g1, kBlock, 0, st>>>((const double*)grid, w.unk, n, w.sc);
+    uint8_t* unk = w.lev[0].m;
+    if (dtype == SMRF_F32) scan_kernel<float><<<g1, kBlock, 0, st>>>((const float*)grid, unk, n, w.sc);
+    else scan_kernel<double><<<g1, kBlock, 0, st>>>((const double*)grid, unk, n, w.sc);
     SMRF_LAUNCH_CHECK();
-    count_launches(1);
+    ++launches;
     unsigned long long counts[2];
     SMRF_CUDA(cudaMemcpyAsync(counts, &w.sc->n_known, sizeof(counts), cudaMemcpyDeviceToHost, st));
     SMRF_CUDA(cudaStreamSynchronize(st));
     const unsigned long long n_unknown = counts[1];
-    if (unknown) SMRF_CUDA(cudaMemcpyAsync(unknown, w.unk, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    if (unknown) SMRF_CUDA(cudaMemcpyAsync(unknown, unk, (size_t)n, cudaMemcpyDeviceToDevice, st));
     int it = 0;
     double rmax = 0.0;
     if (n_unknown > 0) {
-        if (dtype == SMRF_F32) init_u_kernel<float><<<g1, kBlock, 0, st>>>((const float*)grid, w.unk, w.u, n, w.sc);
-        else init_u_kernel<double><<<g1, kBlock, 0, st>>>((const double*)grid, w.unk, w.u, n, w.sc);
+        if (!jacobi) {
+            for (int l = 0; l + 1 < w.nlev; ++l) {
+                Level &f = w.lev[l], &c = w.lev[l + 1];
+                coarsen_kernel<<<tile_grid(c.ny, c.nx), kBlock, 0, st>>>(f.m, c.m, f.ny, f.nx, c.ny, c.nx);
+                ++launches;
+            }
+        }
+        if (dtype == SMRF_F32) init_u_kernel<float><<<g1, kBlock, 0, st>>>((const float*)grid, unk, w.u, n, w.sc);
+        else init_u_kernel<double><<<g1, kBlock, 0, st>>>((const double*)grid, unk, w.u, n, w.sc);
         residual0_kernel<<<g2, kBlock, 0, st>>>(w, ny, nx);
         SMRF_LAUNCH_CHECK();
-        count_launches(2);
+        launches += 2;
         unsigned long long bits = 0;
         SMRF_CUDA(cudaMemcpyAsync(&bits, &w.sc->rmax[0], 8, cudaMemcpyDeviceToHost, st));
         SMRF_CUDA(cudaStreamSynchronize(st));
         memcpy(&rmax, &bits, 8);
+        // The host polls the residual between bursts of iterations; the burst length follows the
+        // observed convergence rate so that few iterations run past the tolerance.
+        double r_prev = rmax;
+        int it_prev = 0, burst = jacobi ? 32 : 4;
         while (rmax > tol && it < max_iter) {
-            int burst = kCheckEvery;
             if (it + burst > max_iter) burst = max_iter - it;
             for (int j = 0; j < burst; ++j, ++it) {
-                p_update_kernel<<<g1, kBlock, 0, st>>>(w, n, it);
+                if (jacobi) {
+                    rz_kernel<true><<<g2, kBlock, 0, st>>>(w, nullptr, ny, nx, it);
+                    p_update_kernel<true><<<g2, kBlock, 0, st>>>(w, nullptr, ny, nx, it);
+                } else {
+                    const float* z = vcycle(w, st, &launches);
+                    rz_kernel<false><<<g2, kBlock, 0, st>>>(w, z, ny, nx, it);
+                    p_update_kernel<false><<<g2, kBlock, 0, st>>>(w, z, ny, nx, it);
+                }
                 apply_kernel<<<g2, kBlock, 0, st>>>(w, ny, nx, it);
                 update_kernel<<<g2, kBlock, 0, st>>>(w, ny, nx, it);
+                launches += 4;
             }
             SMRF_LAUNCH_CHECK();
-            count_launches(3 * burst);
             SMRF_CUDA(cudaMemcpyAsync(&bits, &w.sc->rmax[it], 8, cudaMemcpyDeviceToHost, st));
             SMRF_CUDA(cudaStreamSynchronize(st));
             memcpy(&rmax, &bits, 8);
             if (!(rmax == rmax)) break;   // NaN: give up rather than spin
+            const int cap = jacobi ? 64 : kCheckEvery;
+            int next = cap;
+            if (rmax > tol && rmax > 0.0 && rmax < r_prev && it > it_prev) {
+                const double rate = (log(rmax) - log(r_prev)) / (double)(it - it_prev);   // < 0
+                const double left = (log(tol) - log(rmax)) / rate;
+                next = left < 1.0 ? 1 : (left > (double)cap ? cap : (int)ceil(left));
+            }
+            r_prev = rmax; it_prev = it; burst = next;
         }
-        if (dtype == SMRF_F32) writeback_kernel<float><<<g1, kBlock, 0, st>>>((float*)grid, w.unk, w.u, n);
-        else writeback_kernel<double><<<g1, kBlock, 0, st>>>((double*)grid, w.unk, w.u, n);
+        if (dtype == SMRF_F32) writeback_kernel<float><<<g1, kBlock, 0, st>>>((float*)grid, unk, w.u, n);
+        else writeback_kernel<double><<<g1, kBlock, 0, st>>>((double*)grid, unk, w.u, n);
         SMRF_LAUNCH_CHECK();
-        count_launches(1);
+        ++launches;
         SMRF_CUDA(cudaStreamSynchronize(st));
     }
+    count_launches(launches);
     if (info_host) {
         info_host[0] = (double)it;
         info_host[1] = rmax;

@@ -1,0 +1,93 @@
+"""numpy prototype of the multigrid-preconditioned CG used by the CUDA harmonic inpainter
+(design exploration; not used by the product or the tests)."""
+import sys, time
+import numpy as np
+sys.path.insert(0, '/root/repo')
+from oracle import smrf_oracle as O
+
+def deg_of(shape):
+    ny, nx = shape
+    d = np.full(shape, 4.0)
+    d[0, :] -= 1; d[-1, :] -= 1; d[:, 0] -= 1; d[:, -1] -= 1
+    return d
+
+def applyA(p, unk, deg):
+    # p is zero outside unk
+    s = np.zeros_like(p)
+    s[1:, :] += p[:-1, :]; s[:-1, :] += p[1:, :]; s[:, 1:] += p[:, :-1]; s[:, :-1] += p[:, 1:]
+    return np.where(unk, deg * p - s, 0.0)
+
+def coarsen_mask(unk, mode):
+    ny, nx = unk.shape
+    cy, cx = (ny + 1) // 2, (nx + 1) // 2
+    pad = np.ones((cy * 2, cx * 2), dtype=bool) if mode == 'all' else np.zeros((cy * 2, cx * 2), dtype=bool)
+    pad[:ny, :nx] = unk
+    b = pad.reshape(cy, 2, cx, 2)
+    return b.all(axis=(1, 3)) if mode == 'all' else b.any(axis=(1, 3))
+
+def restrict(r, shape_c):
+    cy, cx = shape_c
+    pad = np.zeros((cy * 2, cx * 2)); pad[:r.shape[0], :r.shape[1]] = r
+    return pad.reshape(cy, 2, cx, 2).sum(axis=(1, 3))
+
+def prolong(e, shape_f):
+    return np.repeat(np.repeat(e, 2, 0), 2, 1)[:shape_f[0], :shape_f[1]]
+
+class MG:
+    def __init__(self, unk, mode='all', nu=2, omega=0.8, min_size=4, scale=1.0):
+        self.levels = []
+        u = unk
+        while True:
+            self.levels.append((u, deg_of(u.shape)))
+            if min(u.shape) <= min_size or not u.any():
+                break
+            u = coarsen_mask(u, mode)
+        self.nu, self.omega, self.scale = nu, omega, scale
+    def smooth(self, l, x, b, n):
+        unk, deg = self.levels[l]
+        for _ in range(n):
+            x = x + self.omega * np.where(unk, (b - applyA(x, unk, deg)) / deg, 0.0)
+        return x
+    def vcycle(self, l, b):
+        unk, deg = self.levels[l]
+        if l == len(self.levels) - 1:
+            return self.smooth(l, np.zeros_like(b), b, 8)
+        x = self.smooth(l, np.zeros_like(b), b, self.nu)
+        r = np.where(unk, b - applyA(x, unk, deg), 0.0)
+        uc, _ = self.levels[l + 1]
+        rc = np.where(uc, restrict(r, uc.shape), 0.0)
+        ec = self.vcycle(l + 1, rc)
+        x = x + np.where(unk, self.scale * prolong(ec, unk.shape), 0.0)
+        return self.smooth(l, x, b, self.nu)
+
+def pcg(A_grid, tol=1e-9, precond='mg', maxit=3000, **kw):
+    unk = np.isnan(A_grid)
+    deg = deg_of(unk.shape)
+    u = np.where(unk, np.nanmean(A_grid), A_grid)
+    s = np.zeros_like(u)
+    s[1:, :] += u[:-1, :]; s[:-1, :] += u[1:, :]; s[:, 1:] += u[:, :-1]; s[:, :-1] += u[:, 1:]
+    r = np.where(unk, s - deg * u, 0.0)
+    mg = MG(unk, **kw) if precond == 'mg' else None
+    M = (lambda r: mg.vcycle(0, r)) if mg else (lambda r: np.where(unk, r / deg, 0.0))
+    z = M(r); p = z.copy(); rz = (r * z).sum(); it = 0
+    while np.abs(r).max() > tol and it < maxit:
+        q = applyA(p, unk, deg)
+        a = rz / (p * q).sum()
+        u += a * p; r -= a * q
+        z = M(r); rz2 = (r * z).sum()
+        p = z + (rz2 / rz) * p; rz = rz2; it += 1
+    return u, it
+
+if __name__ == '__main__':
+    x, y, z, _ = O.synth_cloud(500000, 500.0, 500.0, seed=0)
+    st = {}
+    O.smrf(x, y, z, 1, 18, .15, .5, 1.25, stages=st)
+    for name in ('Zmin_binned', 'Zpro_punched'):
+        G = st[name]
+        ex = O.harmonic_fill_exact(G)
+        t0 = time.time(); u, it = pcg(G, precond='jacobi'); print(name, 'jacobi iters', it, 'err', np.abs(u - ex).max(), '%.1fs' % (time.time() - t0))
+        for mode in ('all', 'any'):
+            for nu in (1, 2):
+                for scale in (1.0, 2.0):
+                    t0 = time.time(); u, it = pcg(G, precond='mg', mode=mode, nu=nu, scale=scale)
+                    print(name, 'mg', mode, 'nu', nu, 'scale', scale, 'iters', it, 'err', np.abs(u - ex).max(), '%.1fs' % (time.time() - t0))
