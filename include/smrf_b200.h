@@ -84,12 +84,20 @@ int smrf_bin_accumulate(const void* x, const void* y, const void* z, int64_t n, 
                         int bin_type, int64_t* out_of_range, void* stream);
 int smrf_bin_finalize(void* grid, uint8_t* empty, int64_t ny, int64_t nx, int dtype, int bin_type,
                       void* stream);
+/* Row-band sharding: every rank bins its own arbitrary slice of the points
+ * into a full-grid replica; smrf_bin_finalize_partial decodes the keys leaving +inf (min) /
+ * -inf (max) in untouched cells, so that an elementwise MIN / MAX reduce-scatter over the
+ * ranks (NCCL) yields each rank's row band of the global binning; smrf_bin_mark_empty then
+ * turns the cells that are still +-inf into NaN and writes the empty mask. */
+int smrf_bin_finalize_partial(void* grid, int64_t ny, int64_t nx, int dtype, int bin_type, void* stream);
+int smrf_bin_mark_empty(void* grid, uint8_t* empty, int64_t ny, int64_t nx, int dtype, int bin_type,
+                        void* stream);
 
 /* ---- inpaint_nans_by_springs --------------------------------- neilpy.py:1227-1271
  * Discrete harmonic fill of the NaN cells of `grid` (in place): for every NaN cell
  * deg*u - sum(NaN nbrs u) = sum(known nbrs a), deg = number of in-grid 4-neighbours
  * (the normal equations of the reference's spring system).  Solved in float64 by
- * preconditioned conjugate gradients entirely in HBM; stops when the
+ * multigrid-preconditioned conjugate gradients entirely in HBM; stops when the
  * max-norm of the residual is <= tol (metres) or after max_iter iterations.
  * A grid with no NaN is returned unchanged; an all-NaN grid becomes zeros (the
  * minimum-norm answer LSQR gives).  `unknown` (optional, may be NULL) receives the
@@ -99,6 +107,35 @@ size_t smrf_inpaint_workspace_bytes(int64_t ny, int64_t nx);
 int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown,
                  void* workspace, size_t workspace_bytes, double tol, int max_iter,
                  double* info_host, void* stream);
+
+/* The same solver, one phase at a time, for a row band whose neighbours live on other
+ * ranks (the caller all-reduces the dot-product slots and exchanges one boundary row of u
+ * (once) and of p (every iteration) between the calls -- neilpy_b200/distributed.py):
+ *   setup  : NaN mask + multigrid hierarchy of the band; statistics of the known cells
+ *   start  : phase 0: u = known value or `guess`;  phase 1: r = b - A u with the
+ *            neighbours' boundary rows of u (u_above / u_below, nx doubles each)
+ *   step   : phase 0: z = M^-1 r (band-local V-cycle), rz[k] += r.z
+ *            phase 1: p = z + (rz[k]/rz[k-1]) p
+ *            phase 2: q = A p with the neighbours' boundary rows of p and of the NaN mask,
+ *                     pq[k] += p.q
+ *            phase 3: u += alpha p, r -= alpha q, rmax[k+1] = max |r|
+ *   finish : write the solution into the NaN cells of `grid`
+ * has_above / has_below say whether a neighbouring band exists (its cells count in the
+ * degree; inside the preconditioner they carry no correction: block Jacobi over bands).
+ * smrf_inpaint_layout reports byte offsets into the workspace: {u plane, p plane, NaN
+ * mask, rz[], pq[], rmax[] (bit patterns of non-negative doubles), statistics block
+ * {sum_known f64, n_known u64, n_unknown u64}, slots per array}. */
+int smrf_inpaint_layout(int64_t ny, int64_t nx, int64_t* out8_host);
+int smrf_inpaint_setup(const void* grid, int64_t ny, int64_t nx, int dtype, void* workspace,
+                       size_t workspace_bytes, int has_above, int has_below, void* stream);
+int smrf_inpaint_start(const void* grid, int64_t ny, int64_t nx, int dtype, void* workspace,
+                       size_t workspace_bytes, int has_above, int has_below, double guess, int phase,
+                       const double* u_above, const double* u_below, void* stream);
+int smrf_inpaint_step(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, int has_above,
+                      int has_below, int k, int phase, const double* p_above, const double* p_below,
+                      const uint8_t* m_above, const uint8_t* m_below, void* stream);
+int smrf_inpaint_finish(void* grid, int64_t ny, int64_t nx, int dtype, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* ---- progressive_filter -------------------------------------- neilpy.py:1659-1680
  * For each radius windows_host[i] (in order): this = opening(last, disk(w));

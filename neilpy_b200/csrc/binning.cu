@@ -127,6 +127,29 @@ __global__ void __launch_bounds__(256) bin_finalize_kernel(T* grid, uint8_t* emp
     }
 }
 
+// row-band sharding: a rank's partial grid keeps +inf (min) / -inf (max) in untouched cells
+// so that an elementwise min/max reduce-scatter over ranks is the global binning
+template <typename T>
+__global__ void __launch_bounds__(256) bin_finalize_inf_kernel(T* grid, int64_t n, int bin_type) {
+    using K = typename KeyOf<T>::type;
+    const K e = bin_type == SMRF_BIN_MIN ? KeyOf<T>::empty_min : KeyOf<T>::empty_max;
+    const T ident = bin_type == SMRF_BIN_MIN ? (T)INFINITY : (T)-INFINITY;
+    K* keys = reinterpret_cast<K*>(grid);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        K k = keys[i];
+        grid[i] = (k == e) ? ident : KeyOf<T>::unkey(k);
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) mark_empty_kernel(T* grid, uint8_t* empty, int64_t n, int bin_type) {
+    const T ident = bin_type == SMRF_BIN_MIN ? (T)INFINITY : (T)-INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool is_empty = grid[i] == ident;
+        if (is_empty) grid[i] = quiet_nan<T>();
+        if (empty) empty[i] = is_empty ? 1 : 0;
+    }
+}
+
 static inline int grid_for(int64_t n, int per_block = 256, int waves = 8) {
     int64_t b = (n + per_block - 1) / per_block;
     int64_t cap = (int64_t)num_sms() * waves;
@@ -252,6 +275,34 @@ int smrf_bin_finalize(void* grid, uint8_t* empty, int64_t ny, int64_t nx, int dt
     int g = grid_for(n, 256, 16);
     if (dtype == SMRF_F32) bin_finalize_kernel<float><<<g, 256, 0, st>>>((float*)grid, empty, n, bin_type);
     else if (dtype == SMRF_F64) bin_finalize_kernel<double><<<g, 256, 0, st>>>((double*)grid, empty, n, bin_type);
+    else SMRF_CHECK_ARG(false, "bad dtype");
+    SMRF_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int smrf_bin_finalize_partial(void* grid, int64_t ny, int64_t nx, int dtype, int bin_type, void* stream) {
+    SMRF_CHECK_ARG(grid, "null grid");
+    SMRF_CHECK_ARG(ny > 0 && nx > 0, "empty grid");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t n = ny * nx;
+    int g = grid_for(n, 256, 16);
+    if (dtype == SMRF_F32) bin_finalize_inf_kernel<float><<<g, 256, 0, st>>>((float*)grid, n, bin_type);
+    else if (dtype == SMRF_F64) bin_finalize_inf_kernel<double><<<g, 256, 0, st>>>((double*)grid, n, bin_type);
+    else SMRF_CHECK_ARG(false, "bad dtype");
+    SMRF_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int smrf_bin_mark_empty(void* grid, uint8_t* empty, int64_t ny, int64_t nx, int dtype, int bin_type, void* stream) {
+    SMRF_CHECK_ARG(grid, "null grid");
+    SMRF_CHECK_ARG(ny > 0 && nx > 0, "empty grid");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t n = ny * nx;
+    int g = grid_for(n, 256, 16);
+    if (dtype == SMRF_F32) mark_empty_kernel<float><<<g, 256, 0, st>>>((float*)grid, empty, n, bin_type);
+    else if (dtype == SMRF_F64) mark_empty_kernel<double><<<g, 256, 0, st>>>((double*)grid, empty, n, bin_type);
     else SMRF_CHECK_ARG(false, "bad dtype");
     SMRF_LAUNCH_CHECK();
     count_launches(1);

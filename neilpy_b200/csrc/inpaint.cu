@@ -52,6 +52,9 @@ struct Ws {
     double *u, *r, *p, *q;
     Scalars* sc;
     int nlev;
+    // row-band sharding: does a neighbouring band exist above row 0 / below row ny-1?  Its cells
+    // count in the degree; inside the preconditioner they are zero-correction (block Jacobi).
+    int has_above, has_below;
     Level lev[kMaxLevels];
 };
 
@@ -72,6 +75,7 @@ static size_t carve(void* workspace, int64_t ny, int64_t nx, Ws* w) {
     const size_t n = (size_t)ny * (size_t)nx;
     const size_t plane = align_up(n * 8);
     Ws t;
+    t.has_above = t.has_below = 0;
     t.u = (double*)b; b += plane;
     t.r = (double*)b; b += plane;
     t.p = (double*)b; b += plane;
@@ -139,8 +143,8 @@ __device__ __forceinline__ int64_t tile_lane() { return threadIdx.x; }
             if (const int64_t X_ = (t__ - Y_ * (T).per_row) * kBlock + tile_lane(); true)   \
                 if (const bool IN_ = X_ < (T).nx; true)
 
-__device__ __forceinline__ int degree(int64_t y, int64_t x, int64_t ny, int64_t nx) {
-    return (y > 0) + (y + 1 < ny) + (x > 0) + (x + 1 < nx);
+__device__ __forceinline__ int degree(int64_t y, int64_t x, int64_t ny, int64_t nx, int above = 0, int below = 0) {
+    return (y > 0 || above) + (y + 1 < ny || below) + (x > 0) + (x + 1 < nx);
 }
 
 // ---- pass 0: NaN mask, statistics of the known cells ------------------------------------
@@ -176,7 +180,8 @@ __global__ void __launch_bounds__(kBlock) init_u_kernel(const T* __restrict__ gr
 
 // r = b - A u on the unknown cells (u holds the known values at known cells, so the
 // right-hand side is implicit); b0 = (float) r feeds the preconditioner; rmax[0] = max |r|
-__global__ void __launch_bounds__(kBlock) residual0_kernel(Ws w, int64_t ny, int64_t nx) {
+__global__ void __launch_bounds__(kBlock) residual0_kernel(Ws w, int64_t ny, int64_t nx, const double* __restrict__ ua,
+                                                           const double* __restrict__ ub) {
     const Tiles T(ny, nx);
     const uint8_t* unk = w.lev[0].m;
     double rm = 0.0;
@@ -187,10 +192,12 @@ __global__ void __launch_bounds__(kBlock) residual0_kernel(Ws w, int64_t ny, int
             if (unk[i]) {
                 double s = 0.0;
                 if (y > 0) s += w.u[i - nx];
+                else if (w.has_above) s += ua[x];
                 if (y + 1 < ny) s += w.u[i + nx];
+                else if (w.has_below) s += ub[x];
                 if (x > 0) s += w.u[i - 1];
                 if (x + 1 < nx) s += w.u[i + 1];
-                const int d = degree(y, x, ny, nx);
+                const int d = degree(y, x, ny, nx, w.has_above, w.has_below);
                 const double r = d ? s - (double)d * w.u[i] : 0.0;
                 w.r[i] = r; w.p[i] = 0.0;
                 rf = (float)r;
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(kBlock) rz_kernel(Ws w, const float* __restric
             const int64_t i = y * nx + x;
             if (unk[i]) {
                 const double r = w.r[i];
-                const int d = degree(y, x, ny, nx);
+                const int d = degree(y, x, ny, nx, w.has_above, w.has_below);
                 const double zi = JACOBI ? (d ? r / (double)d : 0.0) : (double)z[i];
                 rz += r * zi;
             }
@@ -234,7 +241,7 @@ __global__ void __launch_bounds__(kBlock) p_update_kernel(Ws w, const float* __r
         if (in) {
             const int64_t i = y * nx + x;
             if (unk[i]) {
-                const int d = degree(y, x, ny, nx);
+                const int d = degree(y, x, ny, nx, w.has_above, w.has_below);
                 const double zi = JACOBI ? (d ? w.r[i] / (double)d : 0.0) : (double)z[i];
                 w.p[i] = zi + beta * w.p[i];
             }
@@ -243,7 +250,9 @@ __global__ void __launch_bounds__(kBlock) p_update_kernel(Ws w, const float* __r
 }
 
 // q = A p (p is only ever read on unknown cells);  pq[k] = p.q
-__global__ void __launch_bounds__(kBlock) apply_kernel(Ws w, int64_t ny, int64_t nx, int k) {
+__global__ void __launch_bounds__(kBlock) apply_kernel(Ws w, int64_t ny, int64_t nx, int k, const double* __restrict__ pa,
+                                                       const double* __restrict__ pb, const uint8_t* __restrict__ ma,
+                                                       const uint8_t* __restrict__ mb) {
     const Tiles T(ny, nx);
     const uint8_t* unk = w.lev[0].m;
     double pq = 0.0;
@@ -252,12 +261,14 @@ __global__ void __launch_bounds__(kBlock) apply_kernel(Ws w, int64_t ny, int64_t
             const int64_t i = y * nx + x;
             if (unk[i]) {
                 double s = 0.0;
-                if (y > 0 && unk[i - nx]) s += w.p[i - nx];
-                if (y + 1 < ny && unk[i + nx]) s += w.p[i + nx];
+                if (y > 0) { if (unk[i - nx]) s += w.p[i - nx]; }
+                else if (w.has_above && ma[x]) s += pa[x];
+                if (y + 1 < ny) { if (unk[i + nx]) s += w.p[i + nx]; }
+                else if (w.has_below && mb[x]) s += pb[x];
                 if (x > 0 && unk[i - 1]) s += w.p[i - 1];
                 if (x + 1 < nx && unk[i + 1]) s += w.p[i + 1];
                 const double pi = w.p[i];
-                const double q = (double)degree(y, x, ny, nx) * pi - s;
+                const double q = (double)degree(y, x, ny, nx, w.has_above, w.has_below) * pi - s;
                 w.q[i] = q;
                 pq += pi * q;
             }
@@ -323,14 +334,14 @@ __global__ void __launch_bounds__(kBlock) coarsen_kernel(const uint8_t* __restri
 template <bool FIRST>
 __global__ void __launch_bounds__(kBlock) smooth_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                         const float* __restrict__ b, const uint8_t* __restrict__ m,
-                                                        int64_t ny, int64_t nx) {
+                                                        int64_t ny, int64_t nx, int above, int below) {
     const Tiles T(ny, nx);
     SMRF_FOR_TILES(T, y, xx, in) {
         if (in) {
             const int64_t i = y * nx + xx;
             float v = 0.f;
             if (m[i]) {
-                const float d = (float)degree(y, xx, ny, nx);
+                const float d = (float)degree(y, xx, ny, nx, above, below);
                 if (FIRST) {
                     v = d > 0.f ? kOmega * b[i] / d : 0.f;
                 } else {
@@ -351,7 +362,8 @@ __global__ void __launch_bounds__(kBlock) smooth_kernel(const float* __restrict_
 // bc = P^T (b - A x): the sum of the residuals of the (up to four) children
 __global__ void __launch_bounds__(kBlock) restrict_kernel(const float* __restrict__ x, const float* __restrict__ b,
                                                           const uint8_t* __restrict__ mc, float* __restrict__ bc,
-                                                          int64_t fy, int64_t fx, int64_t cy, int64_t cx) {
+                                                          int64_t fy, int64_t fx, int64_t cy, int64_t cx, int above,
+                                                          int below) {
     const Tiles T(cy, cx);
     SMRF_FOR_TILES(T, Y, X, in) {
         if (in) {
@@ -369,7 +381,7 @@ __global__ void __launch_bounds__(kBlock) restrict_kernel(const float* __restric
                             if (y + 1 < fy) s += x[i + fx];
                             if (xx > 0) s += x[i - 1];
                             if (xx + 1 < fx) s += x[i + 1];
-                            acc += b[i] - ((float)degree(y, xx, fy, fx) * x[i] - s);
+                            acc += b[i] - ((float)degree(y, xx, fy, fx, above, below) * x[i] - s);
                         }
                     }
             }
@@ -407,21 +419,21 @@ static const float* vcycle(Ws& w, cudaStream_t st, int* launches) {
     for (int l = 0; l < L; ++l) {
         Level& v = w.lev[l];
         const int g = tile_grid(v.ny, v.nx);
-        smooth_kernel<true><<<g, kBlock, 0, st>>>(nullptr, v.x, v.b, v.m, v.ny, v.nx);
+        smooth_kernel<true><<<g, kBlock, 0, st>>>(nullptr, v.x, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
         ++n;
         if (l == L - 1) {
             float *a = v.x, *b = v.y;
             for (int s = 1; s < kCoarsestSweeps; ++s) {
-                smooth_kernel<false><<<g, kBlock, 0, st>>>(a, b, v.b, v.m, v.ny, v.nx);
+                smooth_kernel<false><<<g, kBlock, 0, st>>>(a, b, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
                 float* t = a; a = b; b = t;
                 ++n;
             }
             cur[l] = a;
         } else {
-            smooth_kernel<false><<<g, kBlock, 0, st>>>(v.x, v.y, v.b, v.m, v.ny, v.nx);
+            smooth_kernel<false><<<g, kBlock, 0, st>>>(v.x, v.y, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
             cur[l] = v.y;
             Level& c = w.lev[l + 1];
-            restrict_kernel<<<tile_grid(c.ny, c.nx), kBlock, 0, st>>>(cur[l], v.b, c.m, c.b, v.ny, v.nx, c.ny, c.nx);
+            restrict_kernel<<<tile_grid(c.ny, c.nx), kBlock, 0, st>>>(cur[l], v.b, c.m, c.b, v.ny, v.nx, c.ny, c.nx, w.has_above, w.has_below);
             n += 2;
         }
     }
@@ -431,8 +443,8 @@ static const float* vcycle(Ws& w, cudaStream_t st, int* launches) {
         float* a = cur[l];
         float* b = (a == v.x) ? v.y : v.x;
         prolong_kernel<<<g, kBlock, 0, st>>>(a, cur[l + 1], v.m, v.ny, v.nx, w.lev[l + 1].nx);
-        smooth_kernel<false><<<g, kBlock, 0, st>>>(a, b, v.b, v.m, v.ny, v.nx);
-        smooth_kernel<false><<<g, kBlock, 0, st>>>(b, a, v.b, v.m, v.ny, v.nx);
+        smooth_kernel<false><<<g, kBlock, 0, st>>>(a, b, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
+        smooth_kernel<false><<<g, kBlock, 0, st>>>(b, a, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
         cur[l] = a;
         n += 3;
     }
@@ -446,11 +458,161 @@ static const float* vcycle(Ws& w, cudaStream_t st, int* launches) {
 using namespace smrf;
 using namespace smrf::inpaint;
 
+static int g1_for(int64_t n) {
+    int g1 = (int)((n + kBlock - 1) / kBlock);
+    int cap = num_sms() * 16;
+    return g1 > cap ? cap : (g1 < 1 ? 1 : g1);
+}
+static bool use_jacobi() {
+    const char* env = getenv("SMRF_INPAINT_PRECOND");
+    return env && strcmp(env, "jacobi") == 0;
+}
+static int check_ws(const char* fn, void* workspace, size_t bytes, int64_t ny, int64_t nx, int has_above, int has_below,
+                    Ws* w) {
+    if (!workspace || ny <= 0 || nx <= 0) {
+        set_error("%s: null workspace or empty grid", fn);
+        return SMRF_E_ARG;
+    }
+    if (bytes < carve(nullptr, ny, nx, nullptr)) {
+        set_error("%s: workspace %zu < %zu bytes", fn, bytes, carve(nullptr, ny, nx, nullptr));
+        return SMRF_E_WORKSPACE;
+    }
+    carve(workspace, ny, nx, w);
+    w->has_above = has_above ? 1 : 0;
+    w->has_below = has_below ? 1 : 0;
+    return 0;
+}
+
 extern "C" {
 
 size_t smrf_inpaint_workspace_bytes(int64_t ny, int64_t nx) {
     if (ny <= 0 || nx <= 0) return 0;
     return carve(nullptr, ny, nx, nullptr);
+}
+
+int smrf_inpaint_layout(int64_t ny, int64_t nx, int64_t* out8_host) {
+    SMRF_CHECK_ARG(out8_host && ny > 0 && nx > 0, "bad argument");
+    Ws w;
+    carve(nullptr, ny, nx, &w);   // pointers relative to a null base = byte offsets
+    out8_host[0] = (int64_t)(uintptr_t)w.u;
+    out8_host[1] = (int64_t)(uintptr_t)w.p;
+    out8_host[2] = (int64_t)(uintptr_t)w.lev[0].m;
+    out8_host[3] = (int64_t)(uintptr_t)&w.sc->rz[0];
+    out8_host[4] = (int64_t)(uintptr_t)&w.sc->pq[0];
+    out8_host[5] = (int64_t)(uintptr_t)&w.sc->rmax[0];
+    out8_host[6] = (int64_t)(uintptr_t)&w.sc->sum_known;   // {sum_known (f64), n_known (u64), n_unknown (u64)}
+    out8_host[7] = (int64_t)kMaxIter;
+    return 0;
+}
+
+int smrf_inpaint_setup(const void* grid, int64_t ny, int64_t nx, int dtype, void* workspace, size_t workspace_bytes,
+                       int has_above, int has_below, void* stream) {
+    SMRF_CHECK_ARG(grid, "null grid");
+    SMRF_CHECK_ARG(dtype == SMRF_F32 || dtype == SMRF_F64, "bad dtype");
+    Ws w;
+    if (int rc = check_ws("smrf_inpaint_setup", workspace, workspace_bytes, ny, nx, has_above, has_below, &w)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = ny * nx;
+    SMRF_CUDA(cudaMemsetAsync(w.sc, 0, sizeof(Scalars), st));
+    if (dtype == SMRF_F32) scan_kernel<float><<<g1_for(n), kBlock, 0, st>>>((const float*)grid, w.lev[0].m, n, w.sc);
+    else scan_kernel<double><<<g1_for(n), kBlock, 0, st>>>((const double*)grid, w.lev[0].m, n, w.sc);
+    int launches = 1;
+    if (!use_jacobi()) {
+        for (int l = 0; l + 1 < w.nlev; ++l) {
+            Level &f = w.lev[l], &c = w.lev[l + 1];
+            coarsen_kernel<<<tile_grid(c.ny, c.nx), kBlock, 0, st>>>(f.m, c.m, f.ny, f.nx, c.ny, c.nx);
+            ++launches;
+        }
+    }
+    SMRF_LAUNCH_CHECK();
+    count_launches(launches);
+    return 0;
+}
+
+int smrf_inpaint_start(const void* grid, int64_t ny, int64_t nx, int dtype, void* workspace, size_t workspace_bytes,
+                       int has_above, int has_below, double guess, int phase, const double* u_above,
+                       const double* u_below, void* stream) {
+    SMRF_CHECK_ARG(grid, "null grid");
+    SMRF_CHECK_ARG(dtype == SMRF_F32 || dtype == SMRF_F64, "bad dtype");
+    SMRF_CHECK_ARG(phase == 0 || phase == 1, "bad phase");
+    Ws w;
+    if (int rc = check_ws("smrf_inpaint_start", workspace, workspace_bytes, ny, nx, has_above, has_below, &w)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = ny * nx;
+    if (phase == 0) {   // u = known value or the starting guess (the caller exchanges boundary rows of u next)
+        // init_u_kernel reads the guess from the statistics block: store it there as a mean over one cell
+        Scalars tmp_stats;
+        (void)tmp_stats;
+        double g = guess;
+        unsigned long long one = 1;
+        SMRF_CUDA(cudaMemcpyAsync(&w.sc->sum_known, &g, 8, cudaMemcpyHostToDevice, st));
+        SMRF_CUDA(cudaMemcpyAsync(&w.sc->n_known, &one, 8, cudaMemcpyHostToDevice, st));
+        if (dtype == SMRF_F32) init_u_kernel<float><<<g1_for(n), kBlock, 0, st>>>((const float*)grid, w.lev[0].m, w.u, n, w.sc);
+        else init_u_kernel<double><<<g1_for(n), kBlock, 0, st>>>((const double*)grid, w.lev[0].m, w.u, n, w.sc);
+    } else {
+        SMRF_CHECK_ARG((!has_above || u_above) && (!has_below || u_below), "missing halo row of u");
+        residual0_kernel<<<tile_grid(ny, nx), kBlock, 0, st>>>(w, ny, nx, u_above, u_below);
+    }
+    SMRF_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
+}
+
+int smrf_inpaint_step(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, int has_above, int has_below,
+                      int k, int phase, const double* p_above, const double* p_below, const uint8_t* m_above,
+                      const uint8_t* m_below, void* stream) {
+    SMRF_CHECK_ARG(k >= 0 && k < kMaxIter, "iteration index out of range");
+    Ws w;
+    if (int rc = check_ws("smrf_inpaint_step", workspace, workspace_bytes, ny, nx, has_above, has_below, &w)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g2 = tile_grid(ny, nx);
+    const bool jacobi = use_jacobi();
+    int launches = 0;
+    const float* z = w.lev[0].y;   // where vcycle() leaves its result
+    switch (phase) {
+        case 0:   // z = M^-1 r (local V-cycle), rz[k] += r.z over this band
+            if (jacobi) rz_kernel<true><<<g2, kBlock, 0, st>>>(w, nullptr, ny, nx, k);
+            else {
+                z = vcycle(w, st, &launches);
+                rz_kernel<false><<<g2, kBlock, 0, st>>>(w, z, ny, nx, k);
+            }
+            ++launches;
+            break;
+        case 1:   // p = z + (rz[k]/rz[k-1]) p      (rz[k] must be complete: all-reduced)
+            if (jacobi) p_update_kernel<true><<<g2, kBlock, 0, st>>>(w, nullptr, ny, nx, k);
+            else p_update_kernel<false><<<g2, kBlock, 0, st>>>(w, z, ny, nx, k);
+            ++launches;
+            break;
+        case 2:   // q = A p with the neighbours' boundary rows of p, pq[k] += p.q over this band
+            SMRF_CHECK_ARG((!has_above || (p_above && m_above)) && (!has_below || (p_below && m_below)), "missing halo row of p");
+            apply_kernel<<<g2, kBlock, 0, st>>>(w, ny, nx, k, p_above, p_below, m_above, m_below);
+            ++launches;
+            break;
+        case 3:   // u += alpha p, r -= alpha q, rmax[k+1] = max|r| over this band   (pq[k] complete)
+            update_kernel<<<g2, kBlock, 0, st>>>(w, ny, nx, k);
+            ++launches;
+            break;
+        default:
+            SMRF_CHECK_ARG(false, "bad phase");
+    }
+    SMRF_LAUNCH_CHECK();
+    count_launches(launches);
+    return 0;
+}
+
+int smrf_inpaint_finish(void* grid, int64_t ny, int64_t nx, int dtype, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    SMRF_CHECK_ARG(grid, "null grid");
+    SMRF_CHECK_ARG(dtype == SMRF_F32 || dtype == SMRF_F64, "bad dtype");
+    Ws w;
+    if (int rc = check_ws("smrf_inpaint_finish", workspace, workspace_bytes, ny, nx, 0, 0, &w)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = ny * nx;
+    if (dtype == SMRF_F32) writeback_kernel<float><<<g1_for(n), kBlock, 0, st>>>((float*)grid, w.lev[0].m, w.u, n);
+    else writeback_kernel<double><<<g1_for(n), kBlock, 0, st>>>((double*)grid, w.lev[0].m, w.u, n);
+    SMRF_LAUNCH_CHECK();
+    count_launches(1);
+    return 0;
 }
 
 int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown, void* workspace,
@@ -459,50 +621,24 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
     SMRF_CHECK_ARG(ny > 0 && nx > 0, "empty grid");
     SMRF_CHECK_ARG(dtype == SMRF_F32 || dtype == SMRF_F64, "bad dtype");
     SMRF_CHECK_ARG(tol >= 0.0, "negative tol");
-    if (workspace_bytes < smrf_inpaint_workspace_bytes(ny, nx)) {
-        set_error("smrf_inpaint: workspace %zu < %zu bytes", workspace_bytes, smrf_inpaint_workspace_bytes(ny, nx));
-        return SMRF_E_WORKSPACE;
-    }
-    if (max_iter <= 0 || max_iter > kMaxIter) max_iter = kMaxIter;
-    const char* env = getenv("SMRF_INPAINT_PRECOND");
-    const bool jacobi = env && strcmp(env, "jacobi") == 0;
+    if (max_iter <= 0 || max_iter > kMaxIter - 1) max_iter = kMaxIter - 1;
+    const bool jacobi = use_jacobi();
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = ny * nx;
+    if (int rc = smrf_inpaint_setup(grid, ny, nx, dtype, workspace, workspace_bytes, 0, 0, stream)) return rc;
     Ws w;
     carve(workspace, ny, nx, &w);
-    SMRF_CUDA(cudaMemsetAsync(w.sc, 0, sizeof(Scalars), st));
-
-    int g1 = (int)((n + kBlock - 1) / kBlock);
-    int cap = num_sms() * 16;
-    if (g1 > cap) g1 = cap;
-    const int g2 = tile_grid(ny, nx);
-    int launches = 0;
-
-    uint8_t* unk = w.lev[0].m;
-    if (dtype == SMRF_F32) scan_kernel<float><<<g1, kBlock, 0, st>>>((const float*)grid, unk, n, w.sc);
-    else scan_kernel<double><<<g1, kBlock, 0, st>>>((const double*)grid, unk, n, w.sc);
-    SMRF_LAUNCH_CHECK();
-    ++launches;
-    unsigned long long counts[2];
-    SMRF_CUDA(cudaMemcpyAsync(counts, &w.sc->n_known, sizeof(counts), cudaMemcpyDeviceToHost, st));
+    struct { double sum; unsigned long long nk, nu; } stats;
+    SMRF_CUDA(cudaMemcpyAsync(&stats, &w.sc->sum_known, sizeof(stats), cudaMemcpyDeviceToHost, st));
     SMRF_CUDA(cudaStreamSynchronize(st));
-    const unsigned long long n_unknown = counts[1];
-    if (unknown) SMRF_CUDA(cudaMemcpyAsync(unknown, unk, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    const unsigned long long n_unknown = stats.nu;
+    if (unknown) SMRF_CUDA(cudaMemcpyAsync(unknown, w.lev[0].m, (size_t)n, cudaMemcpyDeviceToDevice, st));
     int it = 0;
     double rmax = 0.0;
     if (n_unknown > 0) {
-        if (!jacobi) {
-            for (int l = 0; l + 1 < w.nlev; ++l) {
-                Level &f = w.lev[l], &c = w.lev[l + 1];
-                coarsen_kernel<<<tile_grid(c.ny, c.nx), kBlock, 0, st>>>(f.m, c.m, f.ny, f.nx, c.ny, c.nx);
-                ++launches;
-            }
-        }
-        if (dtype == SMRF_F32) init_u_kernel<float><<<g1, kBlock, 0, st>>>((const float*)grid, unk, w.u, n, w.sc);
-        else init_u_kernel<double><<<g1, kBlock, 0, st>>>((const double*)grid, unk, w.u, n, w.sc);
-        residual0_kernel<<<g2, kBlock, 0, st>>>(w, ny, nx);
-        SMRF_LAUNCH_CHECK();
-        launches += 2;
+        const double mean = stats.nk ? stats.sum / (double)stats.nk : 0.0;
+        if (int rc = smrf_inpaint_start(grid, ny, nx, dtype, workspace, workspace_bytes, 0, 0, mean, 0, nullptr, nullptr, stream)) return rc;
+        if (int rc = smrf_inpaint_start(grid, ny, nx, dtype, workspace, workspace_bytes, 0, 0, mean, 1, nullptr, nullptr, stream)) return rc;
         unsigned long long bits = 0;
         SMRF_CUDA(cudaMemcpyAsync(&bits, &w.sc->rmax[0], 8, cudaMemcpyDeviceToHost, st));
         SMRF_CUDA(cudaStreamSynchronize(st));
@@ -513,20 +649,9 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
         int it_prev = 0, burst = jacobi ? 32 : 4;
         while (rmax > tol && it < max_iter) {
             if (it + burst > max_iter) burst = max_iter - it;
-            for (int j = 0; j < burst; ++j, ++it) {
-                if (jacobi) {
-                    rz_kernel<true><<<g2, kBlock, 0, st>>>(w, nullptr, ny, nx, it);
-                    p_update_kernel<true><<<g2, kBlock, 0, st>>>(w, nullptr, ny, nx, it);
-                } else {
-                    const float* z = vcycle(w, st, &launches);
-                    rz_kernel<false><<<g2, kBlock, 0, st>>>(w, z, ny, nx, it);
-                    p_update_kernel<false><<<g2, kBlock, 0, st>>>(w, z, ny, nx, it);
-                }
-                apply_kernel<<<g2, kBlock, 0, st>>>(w, ny, nx, it);
-                update_kernel<<<g2, kBlock, 0, st>>>(w, ny, nx, it);
-                launches += 4;
-            }
-            SMRF_LAUNCH_CHECK();
+            for (int j = 0; j < burst; ++j, ++it)
+                for (int ph = 0; ph < 4; ++ph)
+                    if (int rc = smrf_inpaint_step(ny, nx, workspace, workspace_bytes, 0, 0, it, ph, nullptr, nullptr, nullptr, nullptr, stream)) return rc;
             SMRF_CUDA(cudaMemcpyAsync(&bits, &w.sc->rmax[it], 8, cudaMemcpyDeviceToHost, st));
             SMRF_CUDA(cudaStreamSynchronize(st));
             memcpy(&rmax, &bits, 8);
@@ -540,13 +665,9 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
             }
             r_prev = rmax; it_prev = it; burst = next;
         }
-        if (dtype == SMRF_F32) writeback_kernel<float><<<g1, kBlock, 0, st>>>((float*)grid, unk, w.u, n);
-        else writeback_kernel<double><<<g1, kBlock, 0, st>>>((double*)grid, unk, w.u, n);
-        SMRF_LAUNCH_CHECK();
-        ++launches;
+        if (int rc = smrf_inpaint_finish(grid, ny, nx, dtype, workspace, workspace_bytes, stream)) return rc;
         SMRF_CUDA(cudaStreamSynchronize(st));
     }
-    count_launches(launches);
     if (info_host) {
         info_host[0] = (double)it;
         info_host[1] = rmax;

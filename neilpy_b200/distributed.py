@@ -1,0 +1,310 @@
+"""Row-band sharded SMRF over the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink / NVSwitch).  Every rank holds an
+arbitrary slice of the point cloud; the raster is cut into contiguous row bands, one per
+rank, and every stage exchanges exactly the rows it depends on, so the result is the one
+the single-GPU path (and the reference) produces for the whole cloud:
+
+  extent        all-reduce(min/max) of 4 doubles
+  binning       each rank bins its points into a full-grid replica (+inf in untouched
+                cells), then reduce-scatter(MIN) by row band
+  inpaint       conjugate gradients over all bands (all-reduce of the two dot products and
+                one boundary row of the search direction per iteration); each band is
+                preconditioned by its own multigrid V-cycle (block Jacobi over bands)
+  opening       before window w every band receives 2w rows of the previous window's
+                surface from each neighbour (erosion needs w, the dilation of it another w)
+  slope         1 halo row
+  spline        the row-direction solve is local; the column-direction recurrences contract
+                by 0.268 per row, so 80 halo rows reproduce the global solve to rounding
+  classify      all-gather of the two coefficient grids; each rank classifies its own points
+
+The halo / partition helpers are backend-agnostic (they are exercised with gloo on CPU
+tensors in tests/test_distributed_cpu.py); the compute calls need the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+SPLINE_HALO = 80
+
+
+# ------------------------------------------------------------------ partition + halo helpers
+def rows_per_band(ny, world):
+    return (ny + world - 1) // world
+
+
+def band_bounds(ny, world, rank):
+    """Rows [r0, r1) of the global grid owned by `rank` (equal bands, the last may be short)."""
+    per = rows_per_band(ny, world)
+    r0 = min(rank * per, ny)
+    return r0, min(r0 + per, ny)
+
+
+def check_partition(ny, world, halo):
+    """Every band must be able to serve its neighbours' halos from its own rows."""
+    for r in range(world):
+        r0, r1 = band_bounds(ny, world, r)
+        if r1 - r0 < halo and world > 1:
+            raise ValueError('grid of %d rows is too short for %d bands with a %d-row halo' % (ny, world, halo))
+
+
+def exchange_halo(band, h, group=None):
+    """Send the first / last `h` rows of `band` ([rows, nx]) to the bands above / below and
+    receive theirs.  Returns (above, below): the `h` rows just above band row 0 and just
+    below its last row (None at the global border).  Works for any backend and device."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    above = below = None
+    if world == 1 or h == 0:
+        return above, below
+    if band.shape[0] < h:
+        raise ValueError('band of %d rows cannot serve a %d-row halo' % (band.shape[0], h))
+    ops = []
+    if rank > 0:
+        above = torch.empty((h,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
+        ops.append(dist.P2POp(dist.isend, band[:h].contiguous(), rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, above, rank - 1, group))
+    if rank < world - 1:
+        below = torch.empty((h,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
+        ops.append(dist.P2POp(dist.isend, band[-h:].contiguous(), rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, below, rank + 1, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return above, below
+
+
+def with_halo(band, h, group=None):
+    """[above | band | below] as one tensor and the number of halo rows on top."""
+    above, below = exchange_halo(band, h, group)
+    parts = [t for t in (above, band, below) if t is not None]
+    return (torch.cat(parts, 0) if len(parts) > 1 else band), (h if above is not None else 0)
+
+
+# ------------------------------------------------------------------ device stages
+def _api():
+    from . import _lib, api
+    return _lib, api
+
+
+def _inpaint_band(lib, band, ws, tol, group, max_iter=4000):
+    """Distributed multigrid-preconditioned CG on a row band (see module docstring)."""
+    _lib, api = _api()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ny, nx = band.shape
+    code = api._code(band.dtype)
+    st = api._stream
+    need = lib.smrf_inpaint_workspace_bytes(ny, nx)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=band.device)
+    lay = (C.c_int64 * 8)()
+    _lib.check(lib.smrf_inpaint_layout(ny, nx, lay), 'smrf_inpaint_layout')
+    off_u, off_p, off_m, off_rz, off_pq, off_rmax, off_stats, slots = [int(v) for v in lay]
+    f64 = lambda off, n: ws[off:off + 8 * n].view(torch.float64)
+    i64 = lambda off, n: ws[off:off + 8 * n].view(torch.int64)
+    u = f64(off_u, ny * nx).view(ny, nx)
+    p = f64(off_p, ny * nx).view(ny, nx)
+    m = ws[off_m:off_m + ny * nx].view(ny, nx)
+    rz, pq, rmax = f64(off_rz, slots), f64(off_pq, slots), i64(off_rmax, slots)
+    ha, hb = int(rank > 0), int(rank < world - 1)
+    wp, wn = api._ptr(ws), ws.numel()
+
+    _lib.check(lib.smrf_inpaint_setup(api._ptr(band), ny, nx, code, wp, wn, ha, hb, st()), 'smrf_inpaint_setup')
+    stats = torch.stack([f64(off_stats, 1)[0], i64(off_stats + 8, 2)[0].double(), i64(off_stats + 8, 2)[1].double()])
+    dist.all_reduce(stats, group=group)
+    s_known, n_known, n_unknown = [float(v) for v in stats.cpu()]
+    info = {'iterations': 0, 'residual': 0.0, 'unknown': int(n_unknown)}
+    if n_unknown == 0:
+        return info, ws
+    mean = s_known / n_known if n_known else 0.0
+    m_above, m_below = exchange_halo(m, 1, group)
+    _lib.check(lib.smrf_inpaint_start(api._ptr(band), ny, nx, code, wp, wn, ha, hb, mean, 0, None, None, st()), 'start0')
+    u_above, u_below = exchange_halo(u, 1, group)
+    _lib.check(lib.smrf_inpaint_start(api._ptr(band), ny, nx, code, wp, wn, ha, hb, mean, 1, api._ptr(u_above),
+                                      api._ptr(u_below), st()), 'start1')
+
+    def residual(k):
+        dist.all_reduce(rmax[k:k + 1], op=dist.ReduceOp.MAX, group=group)
+        return float(rmax[k:k + 1].view(torch.float64).item())
+
+    r = residual(0)
+    it, r_prev, it_prev, burst = 0, r, 0, 4
+    while r > tol and it < max_iter:
+        for _ in range(burst):
+            k = it
+            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 0, None, None, None, None, st()), 'step0')
+            dist.all_reduce(rz[k:k + 1], group=group)
+            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 1, None, None, None, None, st()), 'step1')
+            p_above, p_below = exchange_halo(p, 1, group)
+            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 2, api._ptr(p_above), api._ptr(p_below),
+                                             api._ptr(m_above), api._ptr(m_below), st()), 'step2')
+            dist.all_reduce(pq[k:k + 1], group=group)
+            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 3, None, None, None, None, st()), 'step3')
+            it += 1
+        r = residual(it)
+        if not (r == r):
+            break
+        nxt = 8
+        if tol < r < r_prev and it > it_prev:
+            rate = (math.log(r) - math.log(r_prev)) / (it - it_prev)
+            left = (math.log(tol) - math.log(r)) / rate
+            nxt = 1 if left < 1 else (8 if left > 8 else int(math.ceil(left)))
+        r_prev, it_prev, burst = r, it, nxt
+    _lib.check(lib.smrf_inpaint_finish(api._ptr(band), ny, nx, code, wp, wn, st()), 'smrf_inpaint_finish')
+    info.update(iterations=it, residual=r)
+    return info, ws
+
+
+def _open_windows_band(lib, band, windows, thresholds, mask, when, negate, group):
+    """Progressive opening of a row band: 2w halo rows per window from each neighbour."""
+    _lib, api = _api()
+    rows, nx = band.shape
+    code, st = api._code(band.dtype), api._stream
+    cur = band
+    last = None
+    for i, w in enumerate(windows):
+        w = int(w)
+        buf, top = with_halo(cur, 2 * w, group)
+        out = torch.empty_like(buf)
+        tmp = torch.empty_like(buf)
+        # the kernel indexes mask/when with the same rows as `buf`: shift the base so that
+        # buffer row `top` is band row 0 (only rows [top, top + rows) are ever touched)
+        mptr = C.c_void_p(mask.data_ptr() - top * nx)
+        wptr = C.c_void_p(when.data_ptr() - top * nx) if when is not None else None
+        _lib.check(lib.smrf_open_window(api._ptr(buf), api._ptr(out), api._ptr(tmp), mptr, wptr, buf.shape[0], nx,
+                                        code, w, float(thresholds[i]), i, int(negate), top, top + rows, st()),
+                   'smrf_open_window')
+        last = out[top:top + rows]
+        if len(windows) > 1:          # neilpy.py:1675-1676
+            cur = last
+    return last
+
+
+def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_threshold=.5, elevation_scaler=1.25,
+                 low_filter_slope=5, dtype=None, inpaint_tol=None, group=None, gather=False):
+    """`neilpy.smrf` (neilpy.py:1685-1808) over all ranks of `group`.
+
+    points : this rank's slice of the cloud, an (N, 4) float32 CUDA tensor (x, y, z, unused)
+             or a tuple (x, y, z) of equal-length CUDA tensors.
+    Returns a dict: 'Zpro' / 'object_cells' (this rank's row band, or the full grids on
+    every rank if gather=True), 'rows' (the band's global row range), 't' (the transform),
+    'is_object_point' (for this rank's points), 'shape' (global ny, nx), 'info'.
+    """
+    _lib, api = _api()
+    lib = _lib.load()
+    dev = api._device()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    windows = api._windows(windows)
+    tol = api.INPAINT_TOL if inpaint_tol is None else inpaint_tol
+    if isinstance(points, (tuple, list)):
+        pts = api._Points(points[0], points[1], points[2], dev)
+    else:
+        pts = api._Points(points, None, None, dev)
+    tdtype = api._grid_dtype(dtype, pts.default_dtype)
+    code, st = api._code(tdtype), api._stream
+
+    # ---- extent: local min/max, then all-reduce
+    out4 = torch.empty(4, dtype=torch.float64, device=dev)
+    bad = torch.zeros(1, dtype=torch.int64, device=dev)
+    scratch = torch.empty(4, dtype=torch.int64, device=dev)
+    _lib.check(lib.smrf_extent(pts.ptrs[0], pts.ptrs[1], pts.n, pts.fmt, api._ptr(out4), api._ptr(bad),
+                               api._ptr(scratch), st()), 'smrf_extent')
+    lo = torch.stack([out4[0], out4[2]]).nan_to_num(nan=float('inf'))
+    hi = torch.stack([out4[1], out4[3]]).nan_to_num(nan=float('-inf'))
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    dist.all_reduce(bad, group=group)
+    if int(bad.item()):
+        raise ValueError('x and y must be finite')
+    (xmin, ymin), (xmax, ymax) = [float(v) for v in lo.cpu()], [float(v) for v in hi.cpu()]
+    xedges, yedges = api._edges(xmin, xmax, ymin, ymax, cellsize)
+    nx, ny = len(xedges) - 1, len(yedges) - 1
+    wmax = int(windows.max()) if len(windows) else 1
+    check_partition(ny, world, max(2 * wmax, SPLINE_HALO))
+    t = api._make_transform(xedges[0], yedges[0], cellsize)
+    inv6 = api._inverse6(t)
+    per = rows_per_band(ny, world)
+    r0, r1 = band_bounds(ny, world, rank)
+    rows = r1 - r0
+
+    # ---- binning: full-grid replica per rank, reduce-scatter(MIN) to bands
+    replica = torch.empty((per * world, nx), dtype=tdtype, device=dev)
+    oor = torch.zeros(1, dtype=torch.int64, device=dev)
+    _lib.check(lib.smrf_bin_init(api._ptr(replica), per * world, nx, code, _lib.BIN_MIN, st()), 'smrf_bin_init')
+    _lib.check(lib.smrf_bin_accumulate(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, api._ptr(replica),
+                                       ny, nx, code, _lib.BIN_MIN, api._ptr(oor), st()), 'smrf_bin_accumulate')
+    _lib.check(lib.smrf_bin_finalize_partial(api._ptr(replica), per * world, nx, code, _lib.BIN_MIN, st()),
+               'smrf_bin_finalize_partial')
+    padded = torch.empty((per, nx), dtype=tdtype, device=dev)
+    if world > 1:
+        dist.reduce_scatter_tensor(padded, replica, op=dist.ReduceOp.MIN, group=group)
+    else:
+        padded.copy_(replica)
+    del replica
+    Zmin = padded[:rows]
+    empty = torch.empty((rows, nx), dtype=torch.uint8, device=dev)
+    _lib.check(lib.smrf_bin_mark_empty(api._ptr(Zmin), api._ptr(empty), rows, nx, code, _lib.BIN_MIN, st()),
+               'smrf_bin_mark_empty')
+
+    # ---- inpaint, low outliers, progressive filter, punch, inpaint
+    info1, ws = _inpaint_band(lib, Zmin, None, tol, group)
+    low = torch.zeros((rows, nx), dtype=torch.uint8, device=dev)
+    one = np.array([1])
+    _open_windows_band(lib, Zmin, one, low_filter_slope * (one * cellsize), low, None, 1, group)
+    obj = torch.zeros((rows, nx), dtype=torch.uint8, device=dev)
+    if len(windows):
+        _open_windows_band(lib, Zmin, windows, slope_threshold * (windows * cellsize), obj, None, 0, group)
+    object_cells = torch.empty((rows, nx), dtype=torch.uint8, device=dev)
+    _lib.check(lib.smrf_merge_punch(api._ptr(Zmin), api._ptr(empty), api._ptr(low), api._ptr(obj),
+                                    api._ptr(object_cells), rows, nx, code, st()), 'smrf_merge_punch')
+    Zpro = Zmin
+    info2, ws = _inpaint_band(lib, Zpro, ws, tol, group)
+    del ws
+
+    # ---- slope (1 halo row), spline coefficients (SPLINE_HALO rows), all-gather
+    buf, top = with_halo(Zpro, 1, group)
+    Sb = torch.empty_like(buf)
+    _lib.check(lib.smrf_slope(api._ptr(buf), api._ptr(Sb), buf.shape[0], nx, code, float(cellsize), st()), 'smrf_slope')
+    S = Sb[top:top + rows].contiguous()
+    colf = api._factors(nx, dev)
+    rowf_all = api._factors(ny, dev).view(5, ny)
+
+    def coefficients(band):
+        b, tp = with_halo(band, SPLINE_HALO, group)
+        g0 = r0 - tp
+        rf = rowf_all[:, g0:g0 + b.shape[0]].contiguous()
+        wsp = torch.empty(lib.smrf_spline_workspace_bytes(b.shape[0], nx), dtype=torch.uint8, device=dev)
+        c = torch.empty_like(b)
+        _lib.check(lib.smrf_spline_prefilter(api._ptr(b), api._ptr(c), b.shape[0], nx, code, api._ptr(rf),
+                                             api._ptr(colf), api._ptr(wsp), wsp.numel(), st()), 'smrf_spline_prefilter')
+        full = torch.zeros((per * world, nx), dtype=tdtype, device=dev)
+        mine = torch.zeros((per, nx), dtype=tdtype, device=dev)
+        mine[:rows] = c[tp:tp + rows]
+        if world > 1:
+            dist.all_gather_into_tensor(full, mine, group=group)
+        else:
+            full.copy_(mine)
+        return full[:ny]
+
+    coef_z = coefficients(Zpro)
+    coef_s = coefficients(S)
+    is_obj = torch.empty(pts.n, dtype=torch.uint8, device=dev)
+    _lib.check(lib.smrf_classify(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, api._ptr(coef_z),
+                                 api._ptr(coef_s), ny, nx, code, float(elevation_threshold), float(elevation_scaler),
+                                 api._ptr(is_obj), None, None, None, None, st()), 'smrf_classify')
+    res = {'t': t, 'shape': (ny, nx), 'rows': (r0, r1), 'is_object_point': is_obj.view(torch.bool),
+           'info': {'inpaint1': info1, 'inpaint2': info2}}
+    if gather and world > 1:
+        def full(band, fill):
+            mine = torch.full((per, nx), fill, dtype=band.dtype, device=dev)
+            mine[:rows] = band
+            out = torch.empty((per * world, nx), dtype=band.dtype, device=dev)
+            dist.all_gather_into_tensor(out, mine, group=group)
+            return out[:ny]
+        res['Zpro'], res['object_cells'] = full(Zpro, 0), full(object_cells, 0).view(torch.bool)
+    else:
+        res['Zpro'], res['object_cells'] = Zpro, object_cells.view(torch.bool)
+    return res

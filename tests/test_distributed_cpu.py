@@ -1,0 +1,97 @@
+"""The N>1 host logic on CPU: world_size-2 gloo processes exercise the band partition and
+the halo exchange, and show with the oracle's own opening that a band plus 2w halo rows per
+window reproduces the global progressive filter (the rule neilpy_b200.distributed relies on)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from neilpy_b200 import distributed as D
+
+
+def test_band_bounds_cover_the_grid():
+    for ny, world in [(5001, 8), (32769, 8), (100, 3), (7, 2), (16, 1)]:
+        edges = [D.band_bounds(ny, world, r) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == ny
+        assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+        assert max(b - a for a, b in edges) == D.rows_per_band(ny, world)
+    with pytest.raises(ValueError):
+        D.check_partition(100, 4, 40)
+    D.check_partition(5001, 8, 80)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ny, nx, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from oracle import smrf_oracle as O
+        rng = np.random.default_rng(0)
+        Z = np.cumsum(rng.normal(size=(ny, nx)), 0) * 0.3 + rng.normal(size=(ny, nx))
+        Z[20:35, 10:30] += 9.0
+        r0, r1 = D.band_bounds(ny, world, rank)
+        band = torch.from_numpy(Z[r0:r1].copy())
+        # halo exchange returns exactly the neighbours' rows
+        above, below = D.exchange_halo(band, 5)
+        ok = True
+        if rank > 0:
+            ok &= bool(np.array_equal(above.numpy(), Z[r0 - 5:r0]))
+        else:
+            ok &= above is None
+        if rank < world - 1:
+            ok &= bool(np.array_equal(below.numpy(), Z[r1:r1 + 5]))
+        else:
+            ok &= below is None
+        # progressive filter on bands with 2w halo rows per window == global progressive filter
+        windows = np.arange(1, 7)
+        thr = .15 * (windows * 1)
+        ref_mask = O.progressive_filter(Z, windows, 1, .15)
+        cur = band
+        mask = np.zeros((r1 - r0, nx), dtype=bool)
+        for i, w in enumerate(windows):
+            buf, top = D.with_halo(cur, 2 * int(w))
+            b = buf.numpy()
+            # out-of-band rows do not exist for the band: pad with the identities, as the kernels do
+            er = O.ndi.grey_erosion(np.pad(b, w, constant_values=np.inf), footprint=O.disk(w), mode='constant', cval=np.inf)[w:-w, w:-w]
+            # the erosion is only valid w rows inside the buffer; rows outside the image must be -inf for the dilation
+            lo_valid = 0 if top == 0 else w
+            hi_valid = b.shape[0] if (rank == world - 1) else b.shape[0] - w
+            er2 = np.full_like(er, -np.inf)
+            er2[lo_valid:hi_valid] = er[lo_valid:hi_valid]
+            op = O.ndi.grey_dilation(np.pad(er2, w, constant_values=-np.inf), footprint=O.disk(w), mode='constant', cval=-np.inf)[w:-w, w:-w]
+            this = op[top:top + (r1 - r0)]
+            mask |= (cur.numpy() - this) > thr[i]
+            cur = torch.from_numpy(np.ascontiguousarray(this))
+        ok &= bool(np.array_equal(mask, ref_mask[r0:r1]))
+        flag = torch.tensor([1 if ok else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            out.put(int(flag.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_band_halo_rule_with_two_gloo_ranks():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 80, 45, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(150)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) == 1
