@@ -47,10 +47,12 @@ def extent_for(n_points):
     return side, side
 
 
-def make_cloud(n_points, seed):
+def make_cloud(n_points, seed, world=1):
+    """This rank's points: uniform over the whole job area (`world` squares stacked along y),
+    so at N > 1 every rank holds an arbitrary slice of the cloud, not its own band."""
     from neilpy_b200.synth import synth_cloud
     ex, ey = extent_for(n_points)
-    x, y, z, _ = synth_cloud(n_points, ex, ey, seed=seed)
+    x, y, z, _ = synth_cloud(n_points, ex, ey * world, seed=seed)
     out = np.empty((n_points, 4), dtype=np.float32)
     out[:, 0], out[:, 1], out[:, 2], out[:, 3] = x, y, z, 0.0
     return out
@@ -156,7 +158,9 @@ def workload_config(args):
             'points_per_gpu': args.points, 'cellsize': 1, 'windows': 18,
             'l2': 'inputs larger than L2 (point stream %.0f MB, grid planes %.0f MB each)'
                   % (args.points * 16 / 1e6, (ex + 1) * (ey + 1) * 4 / 1e6),
-            'parallelism': 'one cloud per GPU' if args.gpus > 1 else 'single GPU'}
+            'parallelism': ('row bands x%d: reduce-scatter(min) binning, 2w-row halo exchange per window, '
+                            'CG with all-reduced dot products, all-gathered spline coefficients' % args.gpus)
+            if args.gpus > 1 else 'single GPU'}
 
 
 # ------------------------------------------------------------------------------- GPU arm
@@ -240,9 +244,18 @@ def run_gpu(args):
     from neilpy_b200 import _lib
     lib = _lib.load()                                   # fails loudly if the CUDA library is missing
 
-    host = torch.from_numpy(make_cloud(args.points, seed=rank)).pin_memory()
+    host = torch.from_numpy(make_cloud(args.points, seed=rank, world=world)).pin_memory()
     pts = host.to(dev)
     torch.cuda.synchronize()
+    if world > 1:
+        from neilpy_b200.distributed import smrf_sharded, _open_windows_band
+
+        def run(p):
+            r = smrf_sharded(p, **PARAMS)
+            return r['Zpro'], r['t'], r['object_cells'], r['is_object_point']
+    else:
+        def run(p):
+            return nb.smrf(p, **PARAMS)
 
     def barrier():
         if world > 1:
@@ -251,7 +264,7 @@ def run_gpu(args):
 
     # ---- device-resident steps
     for _ in range(args.warmup):
-        nb.smrf(pts, **PARAMS)
+        run(pts)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -259,7 +272,7 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        Z, t, oc, op = nb.smrf(pts, **PARAMS)
+        Z, t, oc, op = run(pts)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
@@ -273,11 +286,16 @@ def run_gpu(args):
 
     # ---- end to end through the public API with host buffers
     e2e_steps = max(1, min(args.steps, 3))
-    out = nb.smrf(host, **PARAMS)                       # warm-up (pinned H2D, pageable D2H)
+    def run_host():
+        if world == 1:
+            return nb.smrf(host, **PARAMS)              # pinned H2D in, pageable D2H out, inside the API
+        Zd, td, ocd, opd = run(host)                    # H2D inside; this rank's band and point mask come back
+        return Zd.cpu().numpy(), td, ocd.cpu().numpy(), opd.cpu().numpy()
+    run_host()                                          # warm-up
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        Zh, th, och, oph = nb.smrf(host, **PARAMS)
+        Zh, th, och, oph = run_host()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1000.0 / e2e_steps
     tms = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -289,17 +307,44 @@ def run_gpu(args):
     e2e = {'value': world * args.points / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps}
 
+    # ---- sharded progressive opening alone (all ranks): Mcells/s of the whole job
+    sharded_open = None
+    if world > 1:
+        windows = np.arange(18) + 1
+        thr = .15 * (windows * 1)
+        mk = torch.zeros(Z.shape, dtype=torch.uint8, device=dev)
+        _open_windows_band(lib, Z, windows, thr, mk, None, 0, None)
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for _ in range(3):
+            _open_windows_band(lib, Z, windows, thr, mk, None, 0, None)
+        o1.record()
+        barrier()
+        tms = torch.tensor([o0.elapsed_time(o1) / 3], dtype=torch.float64, device=dev)
+        cells = torch.tensor([float(Z.numel())], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cells)
+        sharded_open = {'mcells_per_s': float(cells.item()) / (float(tms.item()) * 1e-3) / 1e6,
+                        'ms': float(tms.item()), 'cells': float(cells.item())}
+
     line = None
     if rank == 0:
         # ---- roofline of the opening kernels on this workload's grid, and the C3 opening-only figure
-        stages = {}
-        nb.smrf(pts, return_stages=stages, **PARAMS)
         peaks = load_peaks()
-        roof, extra = opening_roofline(torch, nb, stages['Zmin_filtered'], max(2, min(args.steps, 5)), peaks)
-        extra['inpaint_iterations'] = [stages['inpaint1']['iterations'], stages['inpaint2']['iterations']]
-        extra['grid'] = list(stages['Zpro'].shape)
-        del stages
-        if args.c3:
+        if world == 1:
+            stages = {}
+            nb.smrf(pts, return_stages=stages, **PARAMS)
+            roof, extra = opening_roofline(torch, nb, stages['Zmin_filtered'], max(2, min(args.steps, 5)), peaks)
+            extra['inpaint_iterations'] = [stages['inpaint1']['iterations'], stages['inpaint2']['iterations']]
+            extra['grid'] = list(stages['Zpro'].shape)
+            del stages
+        else:
+            roof, extra = opening_roofline(torch, nb, Z.contiguous(), 2, peaks)   # rank 0's band, no exchange
+            extra['opening_sharded'] = sharded_open
+            extra['opening_mcells_per_s_single_band'] = extra.pop('opening_mcells_per_s')
+            extra['opening_mcells_per_s'] = sharded_open['mcells_per_s']
+        if args.c3 and world == 1:
             try:
                 extra['opening_c3'] = opening_c3(torch, nb, dev, peaks, args.c3)
             except Exception as e:                       # noqa: BLE001  (report, do not hide the main line)

@@ -21,8 +21,9 @@ bool open_march_available(int dtype, int window, int negate) {
 }
 
 const char* open_march_name(int dtype, int window) {
-    (void)dtype; (void)window;
-    return window <= 20 ? "march_f32_fused_c4" : "march_f32_fused_c2";
+    (void)dtype;
+    if (window == 2 || window > 24) return "march_f32_fused";
+    return "march_f32_fused_rowpair";
 }
 
 bool open_force_generic() {

@@ -41,19 +41,24 @@ namespace march {
 constexpr int kRoleThreads = 128;
 constexpr int kThreads = 2 * kRoleThreads;
 
-template <int W>
-struct Cfg {
-    static constexpr int C = W <= 20 ? 4 : 2;                   // adjacent columns per thread
-    static constexpr int U = W <= 4 ? 8 : 4;                    // rows per group (= hand-over batch)
+template <int W_, int C_, bool PAIR_, int MINB_, int U_>
+struct CfgT {
+    static constexpr int W = W_;
+    // PAIR: two incoming rows are folded per step so that every accumulator update is one
+    // 3-input min/max (acc, row u's chord, row u+1's chord) instead of two 2-input ones.  It
+    // needs both rows' neighbourhoods in registers.
+    static constexpr bool PAIR = PAIR_;
+    static constexpr int C = C_;                                // adjacent columns per thread
+    static constexpr int U = U_;                                // rows per group (= hand-over batch)
     static constexpr int A = 2 * W + U;                         // live accumulators per column
     static constexpr int EW = kRoleThreads * C;                 // first-pass columns per CTA
     static constexpr int NL = 2 * W + C;                        // elements a thread reads per row
     static constexpr int NQ = (NL + C - 1) / C;                 // ... as C-wide vectors
     static constexpr int COLS = ((kRoleThreads - 1) * C + NQ * C + 3) / 4 * 4;   // ring row length (floats)
-    static constexpr int XO = ((EW - 2 * W) / 4) * 4;           // output columns per CTA
+    static constexpr int XO = ((EW - 2 * W) / 4) * 4;           // output columns per CTA (multiple of 4 and of C)
     static constexpr int I0 = (2 * W + U - 1) / U * U;          // warm-up rows per pass, whole groups
     static constexpr int NB = 3;                                // batches in the Es ring
-    static constexpr int MINB = W <= 2 ? 3 : (W <= 5 ? 2 : 1);  // CTAs per SM the register budget allows
+    static constexpr int MINB = MINB_;                          // CTAs per SM the register budget is held to
     static constexpr size_t kSmemBytes = (size_t)(2 + NB) * U * COLS * sizeof(float) + 2 * NB * sizeof(uint64_t);
 
     __host__ __device__ static constexpr int isqrt(int v) {
@@ -63,6 +68,17 @@ struct Cfg {
     }
     __host__ __device__ static constexpr int half(int dy) { return isqrt(W * W - dy * dy); }
 };
+
+// The shipped choice per radius, taken from the variant sweep tools/march_sweep.cu on B200
+// (profiles/r1_march_sweep.log).  What matters most is how many warps an SM can hold (the
+// kernel is bound by FMNMX issue and its latency: 2 CTAs/SM whenever ~128 registers suffice),
+// then the number of min/max instructions per cell (PAIR), then shared-memory traffic (C).
+template <int W>
+struct Cfg : CfgT<W,
+                  /*C=*/((W <= 10 || W == 17 || W == 18) ? 4 : 2),
+                  /*PAIR=*/(W != 2 && W <= 24),
+                  /*MINB=*/(W <= 4 ? 1 : (W <= 16 || W == 19 || W == 20 ? 2 : 1)),
+                  /*U=*/4> {};
 
 struct Params {
     const float* in;
@@ -82,6 +98,7 @@ __device__ __forceinline__ void static_for(F&& f) {
         static_for<B + 1, E>(f);
     }
 }
+static_assert(true, "static_for bounds may be negative");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
@@ -150,11 +167,10 @@ __device__ __forceinline__ void store_vec(float* p, const float* src) {
 // dy to acc[u - dy + W]: its first term to acc[u + 2W] (dy = -W, assigned) and the last
 // term of acc[u] (dy = +W), which is returned in `fin`.  srow points at the thread's first
 // element: local index W + c is the centre of column c.
-template <int W, bool IS_MAX, int u>
-__device__ __forceinline__ void chord_step(const float* __restrict__ srow, float (&acc)[Cfg<W>::A][Cfg<W>::C],
-                                           float (&fin)[Cfg<W>::C]) {
-    using K = Cfg<W>;
-    constexpr int C = K::C;
+template <typename K, bool IS_MAX, int u>
+__device__ __forceinline__ void chord_step(const float* __restrict__ srow, float (&acc)[K::A][K::C],
+                                           float (&fin)[K::C]) {
+    constexpr int C = K::C, W = K::W;
     float z[K::NQ * C];
 #pragma unroll
     for (int i = 0; i < K::NQ; ++i) load_vec<C>(srow + i * C, z + i * C);
@@ -182,18 +198,67 @@ __device__ __forceinline__ void chord_step(const float* __restrict__ srow, float
     });
 }
 
+// Two incoming ring rows (u, u+1 of the current group) at once.  Row u contributes the chord
+// of dy to acc[u + W - dy], row u+1 the chord of dy + 1 to the same accumulator, so each
+// accumulator takes one 3-input min/max.  The horizontal windows R_h of both rows grow in
+// lockstep; an update is issued as soon as the wider of its two chords is available.
+// fin0 / fin1 are the output rows completed by row u and row u+1.
+template <typename K, bool IS_MAX, int u>
+__device__ __forceinline__ void chord_pair(const float* __restrict__ srow0, const float* __restrict__ srow1,
+                                           float (&acc)[K::A][K::C], float (&fin0)[K::C], float (&fin1)[K::C]) {
+    constexpr int C = K::C, W = K::W;
+    float z0[K::NQ * C], z1[K::NQ * C];
+#pragma unroll
+    for (int i = 0; i < K::NQ; ++i) {
+        load_vec<C>(srow0 + i * C, z0 + i * C);
+        load_vec<C>(srow1 + i * C, z1 + i * C);
+    }
+    float R0[W + 1][C], R1[W + 1][C];   // statically indexed: only the live windows occupy registers
+    static_for<0, W + 1>([&](auto H) {
+        constexpr int h = decltype(H)::value;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if constexpr (h == 0) {
+                R0[0][c] = z0[W + c];
+                R1[0][c] = z1[W + c];
+                fin0[c] = op2<IS_MAX>(acc[u][c], R0[0][c]);        // row u is dy = +W of output u
+                acc[u + 2 * W + 1][c] = R1[0][c];                  // row u+1 is dy = -W of the newest output
+            } else {
+                R0[h][c] = op3<IS_MAX>(R0[h - 1][c], z0[W + c - h], z0[W + c + h]);
+                R1[h][c] = op3<IS_MAX>(R1[h - 1][c], z1[W + c - h], z1[W + c + h]);
+            }
+        }
+        // accumulator a = u + W - dy  (dy of row u in [-W, W-1]; row u+1 sees dy + 1)
+        static_for<-W, W>([&](auto DY) {
+            constexpr int dy = decltype(DY)::value;
+            constexpr int h0 = K::half(dy < 0 ? -dy : dy);
+            constexpr int h1 = K::half(dy + 1 < 0 ? -(dy + 1) : dy + 1);
+            if constexpr ((h0 > h1 ? h0 : h1) == h) {
+                constexpr int a = u + W - dy;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    if constexpr (dy == -W) acc[a][c] = op2<IS_MAX>(R0[h0][c], R1[h1][c]);   // first terms of output u+2W
+                    else acc[a][c] = op3<IS_MAX>(acc[a][c], R0[h0][c], R1[h1][c]);
+                }
+            }
+        });
+    });
+#pragma unroll
+    for (int c = 0; c < C; ++c) fin1[c] = acc[u + 1][c];   // completed by row u+1 (its dy = +W, folded above at dy = W-1)
+}
+
 // The first-pass warps stream group `g` of `last` rows [zr0 + g*U, +U) into its Zs slot:
 // warp wi copies rows wi, wi+4, ..; VL floats per cp.async (16 / 8 / 4 bytes); anything
 // outside the image is written as `ident`.
-template <int W, int VL>
+template <typename K, int VL>
 __device__ __forceinline__ void issue_group(const Params& p, float* Zs, int g, int64_t zc0, int64_t zr0, float ident,
                                             int wi, int lane) {
-    using K = Cfg<W>;
     constexpr int NCH = K::COLS / VL;
     float* slot = Zs + (size_t)(g & 1) * K::U * K::COLS;
 #pragma unroll
     for (int rr0 = 0; rr0 < K::U; rr0 += 4) {
         const int rr = rr0 + wi;
+        if (rr >= K::U) break;
         const int64_t r = zr0 + (int64_t)g * K::U + rr;
         const bool rowok = r >= 0 && r < p.ny;
         const float* src = p.in + r * p.nx + zc0;
@@ -211,18 +276,17 @@ __device__ __forceinline__ void issue_group(const Params& p, float* Zs, int g, i
     }
 }
 
-template <int W>
+template <typename K>
 __device__ __forceinline__ void issue_group_any(const Params& p, float* Zs, int g, int64_t zc0, int64_t zr0,
                                                 float ident, int wi, int lane) {
-    if (p.vec_ok && (W % 2 == 0)) issue_group<W, 4>(p, Zs, g, zc0, zr0, ident, wi, lane);
-    else if (p.vec_ok) issue_group<W, 2>(p, Zs, g, zc0, zr0, ident, wi, lane);
-    else issue_group<W, 1>(p, Zs, g, zc0, zr0, ident, wi, lane);
+    if (p.vec_ok && (K::W % 2 == 0)) issue_group<K, 4>(p, Zs, g, zc0, zr0, ident, wi, lane);
+    else if (p.vec_ok) issue_group<K, 2>(p, Zs, g, zc0, zr0, ident, wi, lane);
+    else issue_group<K, 1>(p, Zs, g, zc0, zr0, ident, wi, lane);
 }
 
-template <int W, bool NEG>
-__global__ void __launch_bounds__(kThreads, Cfg<W>::MINB) open_march_kernel(const Params p) {
-    using K = Cfg<W>;
-    constexpr int C = K::C, U = K::U, A = K::A;
+template <typename K, bool NEG>
+__global__ void __launch_bounds__(kThreads, K::MINB) open_march_kernel(const Params p) {
+    constexpr int C = K::C, U = K::U, A = K::A, W = K::W;
     constexpr bool E_MAX = NEG;        // erosion of -Z is -(dilation of Z)
     constexpr bool D_MAX = !NEG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -259,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<W>::MINB) open_march_kernel(cons
         // ------------------------------------------------------------- first pass (erosion)
         const int te = tid, wi = tid >> 5, lane = tid & 31;
         const int64_t zc0 = x0 - 2 * W;
-        issue_group_any<W>(p, Zs, 0, zc0, zr0, e_ident, wi, lane);
+        issue_group_any<K>(p, Zs, 0, zc0, zr0, e_ident, wi, lane);
         float acc[A][C];
 #pragma unroll
         for (int s = 0; s < A; ++s)
@@ -277,24 +341,34 @@ __global__ void __launch_bounds__(kThreads, Cfg<W>::MINB) open_march_kernel(cons
         for (int g = 0; g < nZg; ++g) {
             // group g+1 streams in while group g is consumed; its slot was last read in group
             // g-1, which every first-pass thread left through the barrier below
-            if (g + 1 < nZg) issue_group_any<W>(p, Zs, g + 1, zc0, zr0, e_ident, wi, lane);
+            if (g + 1 < nZg) issue_group_any<K>(p, Zs, g + 1, zc0, zr0, e_ident, wi, lane);
             const float* zb = Zs + (size_t)(g & 1) * U * K::COLS + C * te;
             const int kg = g - K::I0 / U;
             const bool emit = kg >= 0;
             if (emit) mbar_wait(&eempty[slot], phase ^ 1);
             float* eb = Es + (size_t)slot * U * K::COLS + C * te;
-            static_for<0, U>([&](auto UU) {
-                constexpr int u = decltype(UU)::value;
-                float fin[C];
-                chord_step<W, E_MAX, u>(zb + u * K::COLS, acc, fin);
-                if (emit) {
-                    const int64_t e = e0 + (int64_t)kg * U + u;
-                    const bool rowok = e >= 0 && e < p.ny;
+            auto put = [&](int u, float (&fin)[C]) {
+                const int64_t e = e0 + (int64_t)kg * U + u;
+                const bool rowok = e >= 0 && e < p.ny;
 #pragma unroll
-                    for (int c = 0; c < C; ++c) fin[c] = (rowok && colok[c]) ? fin[c] : d_ident;
-                    store_vec<C>(eb + u * K::COLS, fin);
-                }
-            });
+                for (int c = 0; c < C; ++c) fin[c] = (rowok && colok[c]) ? fin[c] : d_ident;
+                store_vec<C>(eb + u * K::COLS, fin);
+            };
+            if constexpr (K::PAIR) {
+                static_for<0, U / 2>([&](auto UU) {
+                    constexpr int u = 2 * decltype(UU)::value;
+                    float fin0[C], fin1[C];
+                    chord_pair<K, E_MAX, u>(zb + u * K::COLS, zb + (u + 1) * K::COLS, acc, fin0, fin1);
+                    if (emit) { put(u, fin0); put(u + 1, fin1); }
+                });
+            } else {
+                static_for<0, U>([&](auto UU) {
+                    constexpr int u = decltype(UU)::value;
+                    float fin[C];
+                    chord_step<K, E_MAX, u>(zb + u * K::COLS, acc, fin);
+                    if (emit) put(u, fin);
+                });
+            }
             if (emit) {
                 mbar_arrive(&efull[slot]);
                 if (++slot == K::NB) { slot = 0; phase ^= 1; }
@@ -324,15 +398,14 @@ __global__ void __launch_bounds__(kThreads, Cfg<W>::MINB) open_march_kernel(cons
             mbar_wait(&efull[slot], phase);
             const float* eb = Es + (size_t)slot * U * K::COLS + C * td;
             const int dg = g - K::I0 / U;
-            static_for<0, U>([&](auto UU) {
-                constexpr int u = decltype(UU)::value;
+            // the re-read of `last` is issued before the compute so that its L2 latency hides under it
+            auto fetch = [&](int u, float (&l)[C]) -> bool {
                 const int64_t d = y0 + (int64_t)dg * U + u;
                 const bool emit = dvalid && dg >= 0 && d < y1;
-                const int64_t off = d * p.nx + gx;
-                float l[C];
 #pragma unroll
                 for (int c = 0; c < C; ++c) l[c] = 0.f;
-                if (emit) {   // issue the re-read of `last` before the compute so L2 latency hides under it
+                if (emit) {
+                    const int64_t off = d * p.nx + gx;
                     if (vec) load_vec<C>(p.in + off, l);
                     else {
 #pragma unroll
@@ -340,34 +413,52 @@ __global__ void __launch_bounds__(kThreads, Cfg<W>::MINB) open_march_kernel(cons
                             if (gx + c < p.nx) l[c] = __ldg(p.in + off + c);
                     }
                 }
-                float fin[C];
-                chord_step<W, D_MAX, u>(eb + u * K::COLS, acc, fin);
-                if (emit) {
-                    if (p.out) {
-                        float o[C];
+                return emit;
+            };
+            auto put = [&](int u, const float (&fin)[C], const float (&l)[C]) {
+                const int64_t off = (y0 + (int64_t)dg * U + u) * p.nx + gx;
+                if (p.out) {
+                    float o[C];
 #pragma unroll
-                        for (int c = 0; c < C; ++c) o[c] = NEG ? -fin[c] : fin[c];
-                        if (vec) store_vec<C>(p.out + off, o);
-                        else {
+                    for (int c = 0; c < C; ++c) o[c] = NEG ? -fin[c] : fin[c];
+                    if (vec) store_vec<C>(p.out + off, o);
+                    else {
 #pragma unroll
-                            for (int c = 0; c < C; ++c)
-                                if (gx + c < p.nx) p.out[off + c] = o[c];
-                        }
+                        for (int c = 0; c < C; ++c)
+                            if (gx + c < p.nx) p.out[off + c] = o[c];
                     }
-                    if (p.mask) {
+                }
+                if (p.mask) {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            // (-Z) - open(-Z) == close(Z) - Z exactly
-                            const double df = NEG ? __dsub_rn((double)fin[c], (double)l[c])
-                                                  : __dsub_rn((double)l[c], (double)fin[c]);
-                            if ((gx + c < p.nx) && (df > p.thr)) {
-                                p.mask[off + c] = 1;
-                                if (p.when) p.when[off + c] = (uint8_t)p.widx;
-                            }
+                    for (int c = 0; c < C; ++c) {
+                        // (-Z) - open(-Z) == close(Z) - Z exactly
+                        const double df = NEG ? __dsub_rn((double)fin[c], (double)l[c])
+                                              : __dsub_rn((double)l[c], (double)fin[c]);
+                        if ((gx + c < p.nx) && (df > p.thr)) {
+                            p.mask[off + c] = 1;
+                            if (p.when) p.when[off + c] = (uint8_t)p.widx;
                         }
                     }
                 }
-            });
+            };
+            if constexpr (K::PAIR) {
+                static_for<0, U / 2>([&](auto UU) {
+                    constexpr int u = 2 * decltype(UU)::value;
+                    float l0[C], l1[C], fin0[C], fin1[C];
+                    const bool emit0 = fetch(u, l0), emit1 = fetch(u + 1, l1);
+                    chord_pair<K, D_MAX, u>(eb + u * K::COLS, eb + (u + 1) * K::COLS, acc, fin0, fin1);
+                    if (emit0) put(u, fin0, l0);
+                    if (emit1) put(u + 1, fin1, l1);
+                });
+            } else {
+                static_for<0, U>([&](auto UU) {
+                    constexpr int u = decltype(UU)::value;
+                    float l[C], fin[C];
+                    const bool emit = fetch(u, l);
+                    chord_step<K, D_MAX, u>(eb + u * K::COLS, acc, fin);
+                    if (emit) put(u, fin, l);
+                });
+            }
             mbar_arrive(&eempty[slot]);
             if (++slot == K::NB) { slot = 0; phase ^= 1; }
 #pragma unroll
@@ -380,13 +471,13 @@ __global__ void __launch_bounds__(kThreads, Cfg<W>::MINB) open_march_kernel(cons
 
 }  // namespace march
 
-template <int W, bool NEG>
-int launch_open_march_f32(const float* in, float* out, uint8_t* mask, uint8_t* when, int64_t ny, int64_t nx,
+template <typename K, bool NEG>
+int launch_open_march_cfg(const float* in, float* out, uint8_t* mask, uint8_t* when, int64_t ny, int64_t nx,
                           double thr, int widx, int64_t row_lo, int64_t row_hi, cudaStream_t st) {
-    using K = march::Cfg<W>;
+    constexpr int W = K::W;
     static bool attr_set = false;
     if (!attr_set) {
-        SMRF_CUDA(cudaFuncSetAttribute(march::open_march_kernel<W, NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SMRF_CUDA(cudaFuncSetAttribute(march::open_march_kernel<K, NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)K::kSmemBytes));
         attr_set = true;
     }
@@ -415,10 +506,16 @@ int launch_open_march_f32(const float* in, float* out, uint8_t* mask, uint8_t* w
     p.seg = seg; p.thr = thr; p.widx = widx;
     p.vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (out == nullptr || ((uintptr_t)out & 15) == 0);
     dim3 grid((unsigned)nstrips, (unsigned)nsegs);
-    march::open_march_kernel<W, NEG><<<grid, march::kThreads, K::kSmemBytes, st>>>(p);
+    march::open_march_kernel<K, NEG><<<grid, march::kThreads, K::kSmemBytes, st>>>(p);
     SMRF_LAUNCH_CHECK();
     count_launches(1);
     return 0;
+}
+
+template <int W, bool NEG>
+int launch_open_march_f32(const float* in, float* out, uint8_t* mask, uint8_t* when, int64_t ny, int64_t nx,
+                          double thr, int widx, int64_t row_lo, int64_t row_hi, cudaStream_t st) {
+    return launch_open_march_cfg<march::Cfg<W>, NEG>(in, out, mask, when, ny, nx, thr, widx, row_lo, row_hi, st);
 }
 
 }  // namespace smrf
