@@ -101,10 +101,12 @@ int smrf_bin_mark_empty(void* grid, uint8_t* empty, int64_t ny, int64_t nx, int 
  * max-norm of the residual is <= tol (metres) or after max_iter iterations.
  * A grid with no NaN is returned unchanged; an all-NaN grid becomes zeros (the
  * minimum-norm answer LSQR gives).  `unknown` (optional, may be NULL) receives the
- * NaN mask.  info_host[0] = iterations, info_host[1] = final residual max-norm,
+ * NaN mask.  `guess` (optional, ny*nx elements of `dtype`) seeds the NaN cells; without it
+ * they start from the mean of the known cells (the answer does not depend on it, the
+ * iteration count does: smrf() passes the last opened surface).  info_host[0] = iterations, info_host[1] = final residual max-norm,
  * info_host[2] = number of unknown cells.  Synchronises `stream`. */
 size_t smrf_inpaint_workspace_bytes(int64_t ny, int64_t nx);
-int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown,
+int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown, const void* guess,
                  void* workspace, size_t workspace_bytes, double tol, int max_iter,
                  double* info_host, void* stream);
 
@@ -112,7 +114,7 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
  * ranks (the caller all-reduces the dot-product slots and exchanges one boundary row of u
  * (once) and of p (every iteration) between the calls -- neilpy_b200/distributed.py):
  *   setup  : NaN mask + multigrid hierarchy of the band; statistics of the known cells
- *   start  : phase 0: u = known value or `guess`;  phase 1: r = b - A u with the
+ *   start  : phase 0: u = known value, else guess_grid (if given), else `guess`;  phase 1: r = b - A u with the
  *            neighbours' boundary rows of u (u_above / u_below, nx doubles each)
  *   step   : phase 0: z = M^-1 r (band-local V-cycle), rz[k] += r.z
  *            phase 1: p = z + (rz[k]/rz[k-1]) p
@@ -129,8 +131,9 @@ int smrf_inpaint_layout(int64_t ny, int64_t nx, int64_t* out8_host);
 int smrf_inpaint_setup(const void* grid, int64_t ny, int64_t nx, int dtype, void* workspace,
                        size_t workspace_bytes, int has_above, int has_below, void* stream);
 int smrf_inpaint_start(const void* grid, int64_t ny, int64_t nx, int dtype, void* workspace,
-                       size_t workspace_bytes, int has_above, int has_below, double guess, int phase,
-                       const double* u_above, const double* u_below, void* stream);
+                       size_t workspace_bytes, int has_above, int has_below, double guess,
+                       const void* guess_grid, int phase, const double* u_above, const double* u_below,
+                       void* stream);
 int smrf_inpaint_step(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, int has_above,
                       int has_below, int k, int phase, const double* p_above, const double* p_below,
                       const uint8_t* m_above, const uint8_t* m_below, void* stream);

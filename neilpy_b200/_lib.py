@@ -35,10 +35,10 @@ SIGNATURES = {
     'smrf_inpaint_workspace_bytes': (_sz, [_i64, _i64]),
     'smrf_inpaint_layout': (_i32, [_i64, _i64, C.POINTER(C.c_int64)]),
     'smrf_inpaint_setup': (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _i32, _i32, _vp]),
-    'smrf_inpaint_start': (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _i32, _i32, _dbl, _i32, _vp, _vp, _vp]),
+    'smrf_inpaint_start': (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _i32, _i32, _dbl, _vp, _i32, _vp, _vp, _vp]),
     'smrf_inpaint_step': (_i32, [_i64, _i64, _vp, _sz, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     'smrf_inpaint_finish': (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _vp]),
-    'smrf_inpaint': (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _sz, _dbl, _i32, _dp, _vp]),
+    'smrf_inpaint': (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _dbl, _i32, _dp, _vp]),
     'smrf_open_workspace_bytes': (_sz, [_i64, _i64, _i32, _i32]),
     'smrf_progressive_open': (_i32, [_vp, _vp, _sz, _vp, _vp, _i64, _i64, _i32, _ip, _dp, _i32, _i32, _vp, _vp]),
     'smrf_open_window': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _dbl, _i32, _i32, _i64, _i64, _vp]),

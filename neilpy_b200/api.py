@@ -30,7 +30,8 @@ from .affine import Affine
 
 __all__ = ['smrf', 'create_dem', 'progressive_filter', 'inpaint_nans_by_springs', 'Affine']
 
-INPAINT_TOL = 1e-9       # metres, max-norm of the residual deg*u - sum(nbrs)
+INPAINT_TOL = 1e-9       # metres, max-norm of the residual deg*u - sum(nbrs): <= 1e-6 m from the exact fill
+SMRF_INPAINT_TOL = 1e-7  # inside smrf(): <= ~1e-4 m from the exact fill, 100x tighter than the reference's own LSQR
 INPAINT_MAX_ITER = 1 << 15
 
 
@@ -182,22 +183,39 @@ def _bin(lib, pts, dev, tdtype, cellsize, bin_type, edges):
     return grid, empty, t, inv6, cellsize
 
 
+_pinned = {}
+
+
+def _to_host(t):
+    """Device tensor -> numpy through a cached pinned staging buffer (pageable D2H copies run at
+    a fraction of the link rate)."""
+    key = (t.dtype, t.numel())
+    buf = _pinned.get(key)
+    if buf is None:
+        if len(_pinned) > 16:
+            _pinned.clear()
+        buf = _pinned[key] = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+    buf.copy_(t.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return buf.numpy().reshape(tuple(t.shape)).copy()
+
+
 def _workspace(nbytes, dev):
     return torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
 
 
-def _inpaint(lib, grid, ws, tol, unknown=None):
+def _inpaint(lib, grid, ws, tol, unknown=None, guess=None):
     ny, nx = grid.shape
     need = lib.smrf_inpaint_workspace_bytes(ny, nx)
     if ws is None or ws.numel() < need:
         ws = _workspace(need, grid.device)
     info = (C.c_double * 3)()
-    _lib.check(lib.smrf_inpaint(_ptr(grid), ny, nx, _code(grid.dtype), _ptr(unknown), _ptr(ws), ws.numel(),
+    _lib.check(lib.smrf_inpaint(_ptr(grid), ny, nx, _code(grid.dtype), _ptr(unknown), _ptr(guess), _ptr(ws), ws.numel(),
                                 float(tol), INPAINT_MAX_ITER, info, _stream()), 'smrf_inpaint')
     return {'iterations': int(info[0]), 'residual': float(info[1]), 'unknown': int(info[2])}
 
 
-def _progressive(lib, surface, windows, thresholds, mask, when, ws, negate=0):
+def _progressive(lib, surface, windows, thresholds, mask, when, ws, negate=0, last_out=None):
     ny, nx = surface.shape
     need = lib.smrf_open_workspace_bytes(ny, nx, _code(surface.dtype), int(max(windows)) if len(windows) else 0)
     if ws is None or ws.numel() < need:
@@ -205,7 +223,7 @@ def _progressive(lib, surface, windows, thresholds, mask, when, ws, negate=0):
     w = (C.c_int32 * len(windows))(*[int(v) for v in windows])
     th = (C.c_double * len(windows))(*[float(v) for v in thresholds])
     _lib.check(lib.smrf_progressive_open(_ptr(surface), _ptr(ws), ws.numel(), _ptr(mask), _ptr(when), ny, nx,
-                                         _code(surface.dtype), w, th, len(windows), negate, None, _stream()),
+                                         _code(surface.dtype), w, th, len(windows), negate, _ptr(last_out), _stream()),
                'smrf_progressive_open')
 
 
@@ -306,7 +324,7 @@ def progressive_filter(Z, windows, cellsize=1, slope_threshold=.15, return_when_
 
 def smrf(x, y=None, z=None, cellsize=1, windows=5, slope_threshold=.15, elevation_threshold=.5,
          elevation_scaler=1.25, low_filter_slope=5, low_outlier_fill=False, return_extras=False,
-         dtype=None, inpaint_tol=INPAINT_TOL, return_stages=None):
+         dtype=None, inpaint_tol=SMRF_INPAINT_TOL, return_stages=None):
     """neilpy.smrf (neilpy.py:1685-1808).
 
     Returns (Zpro, t, object_cells, is_object_point) [+ extras dict].  `return_stages`, if a
@@ -347,8 +365,11 @@ def smrf(x, y=None, z=None, cellsize=1, windows=5, slope_threshold=.15, elevatio
     # --- the progressive morphological filter (:1752-1755)
     obj = torch.zeros((ny, nx), dtype=torch.uint8, device=dev)
     drop = torch.zeros((ny, nx), dtype=torch.uint8, device=dev) if return_extras else None
+    opened = None
     if len(windows):
-        _progressive(lib, Zmin, windows, slope_threshold * (windows * cellsize), obj, drop, ws)
+        # the last opening is the surface with the objects shaved off: the seed of the second inpaint
+        opened = torch.empty_like(Zmin)
+        _progressive(lib, Zmin, windows, slope_threshold * (windows * cellsize), obj, drop, ws, last_out=opened)
     if stages is not None:
         stages['progressive_cells'] = obj.clone()
     # --- object_cells = empty | low | obj; Zpro[object_cells] = nan; second inpaint (:1758-1764)
@@ -358,7 +379,8 @@ def smrf(x, y=None, z=None, cellsize=1, windows=5, slope_threshold=.15, elevatio
                'smrf_merge_punch')
     if stages is not None:
         stages['Zpro_punched'] = Zpro.clone()
-    info2 = _inpaint(lib, Zpro, ws, inpaint_tol)
+    info2 = _inpaint(lib, Zpro, ws, inpaint_tol, guess=opened)
+    del opened
     # --- slope raster (:1785-1786) and the two interpolating splines (:1773, :1788)
     S = torch.empty_like(Zpro)
     _lib.check(lib.smrf_slope(_ptr(Zpro), _ptr(S), ny, nx, code, float(cellsize), st), 'smrf_slope')
@@ -390,9 +412,9 @@ def smrf(x, y=None, z=None, cellsize=1, windows=5, slope_threshold=.15, elevatio
         zvals = pts.a[:, 2].to(torch.float64) if pts.fmt == _lib.PTS_XYZW_F32 else pts.z.to(torch.float64)
         extras = {'above_ground_height': zvals - elev, 'drop_raster': drop, 'when_dropped': when_pt}
     if not pts.on_device:
-        Zpro = Zpro.cpu().numpy()
-        object_cells = object_cells.cpu().numpy()
-        is_obj = is_obj.cpu().numpy()
+        Zpro = _to_host(Zpro)
+        object_cells = _to_host(object_cells)
+        is_obj = _to_host(is_obj)
         if pts.index is not None:
             import pandas as pd
             is_obj = pd.Series(is_obj, index=pts.index)

@@ -31,7 +31,7 @@ constexpr int kCheckEvery = 8;
 constexpr int kBlock = 256;
 constexpr int kMaxLevels = 20;
 constexpr float kOmega = 0.8f;
-constexpr int kCoarsestSweeps = 8;
+constexpr int kCoarsestSweeps = 8;   // even: the coarsest result lands in Level::y
 
 struct Scalars {          // device-resident, indexed by iteration
     double rz[kMaxIter + 2];
@@ -126,22 +126,26 @@ __device__ __forceinline__ double block_max(double v) {
     return t;
 }
 
-// Tiles of one row x 256 columns, walked with a block stride: a few thousand CTAs whatever
-// the grid size, so the per-block atomics of the reductions stay cheap.
+// Tiles of kRows rows x 256 columns, walked with a block stride: a few thousand CTAs whatever
+// the grid size, so the per-block atomics of the reductions stay cheap, and one div/mod per
+// tile rather than per row.
+constexpr int kRows = 4;
 struct Tiles {
     int64_t ny, nx, per_row, total;
     __host__ __device__ Tiles(int64_t ny_, int64_t nx_)
-        : ny(ny_), nx(nx_), per_row((nx_ + kBlock - 1) / kBlock), total(ny_ * ((nx_ + kBlock - 1) / kBlock)) {}
+        : ny(ny_), nx(nx_), per_row((nx_ + kBlock - 1) / kBlock),
+          total(((ny_ + kRows - 1) / kRows) * ((nx_ + kBlock - 1) / kBlock)) {}
 };
-// body sees: int64_t Y_, X_ (tile row, column of this thread); bool IN_ (X_ < nx)
+// body sees: int64_t Y_, X_ (row, column of this thread); bool IN_ (X_ < nx)
 __device__ __forceinline__ int64_t tile_first() { return blockIdx.x; }
 __device__ __forceinline__ int64_t tile_step() { return gridDim.x; }
 __device__ __forceinline__ int64_t tile_lane() { return threadIdx.x; }
-#define SMRF_FOR_TILES(T, Y_, X_, IN_)                                                      \
-    for (int64_t t__ = tile_first(); t__ < (T).total; t__ += tile_step())                   \
-        if (const int64_t Y_ = t__ / (T).per_row; true)                                     \
-            if (const int64_t X_ = (t__ - Y_ * (T).per_row) * kBlock + tile_lane(); true)   \
-                if (const bool IN_ = X_ < (T).nx; true)
+#define SMRF_FOR_TILES(T, Y_, X_, IN_)                                                         \
+    for (int64_t t__ = tile_first(); t__ < (T).total; t__ += tile_step())                      \
+        if (const int64_t ty__ = t__ / (T).per_row; true)                                      \
+            if (const int64_t X_ = (t__ - ty__ * (T).per_row) * kBlock + tile_lane(); true)    \
+                if (const bool IN_ = X_ < (T).nx; true)                                        \
+                    for (int64_t Y_ = ty__ * kRows, ye__ = (Y_ + kRows < (T).ny ? Y_ + kRows : (T).ny); Y_ < ye__; ++Y_)
 
 __device__ __forceinline__ int degree(int64_t y, int64_t x, int64_t ny, int64_t nx, int above = 0, int below = 0) {
     return (y > 0 || above) + (y + 1 < ny || below) + (x > 0) + (x + 1 < nx);
@@ -172,10 +176,22 @@ __global__ void __launch_bounds__(kBlock) scan_kernel(const T* __restrict__ grid
 // ---- u = known value, or the mean of the known cells as the starting guess ---------------
 template <typename T>
 __global__ void __launch_bounds__(kBlock) init_u_kernel(const T* __restrict__ grid, const uint8_t* __restrict__ unk,
-                                                        double* __restrict__ u, int64_t n, const Scalars* sc) {
+                                                        double* __restrict__ u, int64_t n, const Scalars* sc,
+                                                        const T* __restrict__ guess) {
     const double mean = sc->n_known ? sc->sum_known / (double)sc->n_known : 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
-        u[i] = unk[i] ? mean : (double)grid[i];
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        double v;
+        if (unk[i]) {
+            v = mean;
+            if (guess) {
+                const double g = (double)guess[i];
+                if (g == g && fabs(g) < 1e300) v = g;   // a NaN / inf guess falls back to the mean
+            }
+        } else {
+            v = (double)grid[i];
+        }
+        u[i] = v;
+    }
 }
 
 // r = b - A u on the unknown cells (u holds the known values at known cells, so the
@@ -210,20 +226,44 @@ __global__ void __launch_bounds__(kBlock) residual0_kernel(Ws w, int64_t ny, int
     if (threadIdx.x == 0) atomicMax(&w.sc->rmax[0], (unsigned long long)__double_as_longlong(rm));
 }
 
+// The four CG kernels below give every thread one column of a kRows-row tile and keep the
+// tile's values in registers: all loads of a tile are issued before any arithmetic (the
+// kernels are latency-bound otherwise: ncu showed 70-90 % long-scoreboard stalls with one
+// dependent load chain per cell).
+#define SMRF_FOR_TILE_BLOCKS(T, Y0_, X_, IN_)                                                 \
+    for (int64_t t__ = tile_first(); t__ < (T).total; t__ += tile_step())                     \
+        if (const int64_t ty__ = t__ / (T).per_row; true)                                     \
+            if (const int64_t X_ = (t__ - ty__ * (T).per_row) * kBlock + tile_lane(); true)   \
+                if (const bool IN_ = X_ < (T).nx; true)                                       \
+                    if (const int64_t Y0_ = ty__ * kRows; true)
+
 // rz[k] = r.z, then p = z + beta p with beta = rz[k] / rz[k-1] needs the finished sum: two kernels.
 template <bool JACOBI>
 __global__ void __launch_bounds__(kBlock) rz_kernel(Ws w, const float* __restrict__ z, int64_t ny, int64_t nx, int k) {
     const Tiles T(ny, nx);
-    const uint8_t* unk = w.lev[0].m;
+    const uint8_t* __restrict__ unk = w.lev[0].m;
     double rz = 0.0;
-    SMRF_FOR_TILES(T, y, x, in) {
+    SMRF_FOR_TILE_BLOCKS(T, y0, x, in) {
         if (in) {
-            const int64_t i = y * nx + x;
-            if (unk[i]) {
-                const double r = w.r[i];
-                const int d = degree(y, x, ny, nx, w.has_above, w.has_below);
-                const double zi = JACOBI ? (d ? r / (double)d : 0.0) : (double)z[i];
-                rz += r * zi;
+            uint8_t mk[kRows];
+            double rv[kRows];
+            float zv[kRows];
+            const int64_t i0 = y0 * nx + x;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) mk[r] = (y0 + r < ny) ? unk[i0 + r * nx] : 0;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                rv[r] = mk[r] ? w.r[i0 + r * nx] : 0.0;
+                zv[r] = (!JACOBI && mk[r]) ? z[i0 + r * nx] : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                if (JACOBI) {
+                    const int d = degree(y0 + r, x, ny, nx, w.has_above, w.has_below);
+                    if (mk[r] && d) rz += rv[r] * (rv[r] / (double)d);
+                } else {
+                    rz += rv[r] * (double)zv[r];
+                }
             }
         }
     }
@@ -235,16 +275,30 @@ template <bool JACOBI>
 __global__ void __launch_bounds__(kBlock) p_update_kernel(Ws w, const float* __restrict__ z, int64_t ny, int64_t nx,
                                                           int k) {
     const Tiles T(ny, nx);
-    const uint8_t* unk = w.lev[0].m;
+    const uint8_t* __restrict__ unk = w.lev[0].m;
     const double beta = (k == 0 || w.sc->rz[k - 1] == 0.0) ? 0.0 : w.sc->rz[k] / w.sc->rz[k - 1];
-    SMRF_FOR_TILES(T, y, x, in) {
+    SMRF_FOR_TILE_BLOCKS(T, y0, x, in) {
         if (in) {
-            const int64_t i = y * nx + x;
-            if (unk[i]) {
-                const int d = degree(y, x, ny, nx, w.has_above, w.has_below);
-                const double zi = JACOBI ? (d ? w.r[i] / (double)d : 0.0) : (double)z[i];
-                w.p[i] = zi + beta * w.p[i];
+            uint8_t mk[kRows];
+            double zv[kRows], pv[kRows];
+            const int64_t i0 = y0 * nx + x;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) mk[r] = (y0 + r < ny) ? unk[i0 + r * nx] : 0;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                if (mk[r]) {
+                    pv[r] = w.p[i0 + r * nx];
+                    if (JACOBI) {
+                        const int d = degree(y0 + r, x, ny, nx, w.has_above, w.has_below);
+                        zv[r] = d ? w.r[i0 + r * nx] / (double)d : 0.0;
+                    } else {
+                        zv[r] = (double)z[i0 + r * nx];
+                    }
+                }
             }
+#pragma unroll
+            for (int r = 0; r < kRows; ++r)
+                if (mk[r]) w.p[i0 + r * nx] = zv[r] + beta * pv[r];
         }
     }
 }
@@ -254,23 +308,51 @@ __global__ void __launch_bounds__(kBlock) apply_kernel(Ws w, int64_t ny, int64_t
                                                        const double* __restrict__ pb, const uint8_t* __restrict__ ma,
                                                        const uint8_t* __restrict__ mb) {
     const Tiles T(ny, nx);
-    const uint8_t* unk = w.lev[0].m;
+    const uint8_t* __restrict__ unk = w.lev[0].m;
+    const double* __restrict__ p = w.p;
     double pq = 0.0;
-    SMRF_FOR_TILES(T, y, x, in) {
+    SMRF_FOR_TILE_BLOCKS(T, y0, x, in) {
         if (in) {
-            const int64_t i = y * nx + x;
-            if (unk[i]) {
-                double s = 0.0;
-                if (y > 0) { if (unk[i - nx]) s += w.p[i - nx]; }
-                else if (w.has_above && ma[x]) s += pa[x];
-                if (y + 1 < ny) { if (unk[i + nx]) s += w.p[i + nx]; }
-                else if (w.has_below && mb[x]) s += pb[x];
-                if (x > 0 && unk[i - 1]) s += w.p[i - 1];
-                if (x + 1 < nx && unk[i + 1]) s += w.p[i + 1];
-                const double pi = w.p[i];
-                const double q = (double)degree(y, x, ny, nx, w.has_above, w.has_below) * pi - s;
-                w.q[i] = q;
-                pq += pi * q;
+            // slot j <-> row y0 + j - 1: the column of the tile plus one row above and below
+            uint8_t mk[kRows + 2], ml[kRows], mr[kRows];
+            double pv[kRows + 2], pl[kRows], pr[kRows];
+            const int64_t i0 = y0 * nx + x;
+#pragma unroll
+            for (int j = 0; j < kRows + 2; ++j) {
+                const int64_t y = y0 + j - 1;
+                uint8_t m = 0;
+                if (y >= 0 && y < ny) m = unk[i0 + (int64_t)(j - 1) * nx];
+                else if (y < 0 && w.has_above) m = ma[x];
+                else if (y == ny && w.has_below) m = mb[x];
+                mk[j] = m;
+            }
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                const bool me = mk[r + 1] != 0;
+                ml[r] = (me && x > 0) ? unk[i0 + r * nx - 1] : 0;
+                mr[r] = (me && x + 1 < nx) ? unk[i0 + r * nx + 1] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < kRows + 2; ++j) {
+                const int64_t y = y0 + j - 1;
+                double v = 0.0;
+                if (mk[j]) v = (y < 0) ? pa[x] : ((y >= ny) ? pb[x] : p[i0 + (int64_t)(j - 1) * nx]);
+                pv[j] = v;
+            }
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                pl[r] = ml[r] ? p[i0 + r * nx - 1] : 0.0;
+                pr[r] = mr[r] ? p[i0 + r * nx + 1] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                if (mk[r + 1] && y0 + r < ny) {
+                    const double pi = pv[r + 1];
+                    const double sum = pv[r] + pv[r + 2] + pl[r] + pr[r];
+                    const double q = (double)degree(y0 + r, x, ny, nx, w.has_above, w.has_below) * pi - sum;
+                    w.q[i0 + r * nx] = q;
+                    pq += pi * q;
+                }
             }
         }
     }
@@ -281,19 +363,33 @@ __global__ void __launch_bounds__(kBlock) apply_kernel(Ws w, int64_t ny, int64_t
 // u += alpha p; r -= alpha q; b0 = (float) r; rmax[k+1] = max |r|
 __global__ void __launch_bounds__(kBlock) update_kernel(Ws w, int64_t ny, int64_t nx, int k) {
     const Tiles T(ny, nx);
-    const uint8_t* unk = w.lev[0].m;
+    const uint8_t* __restrict__ unk = w.lev[0].m;
     const double pqk = w.sc->pq[k];
     const double alpha = pqk != 0.0 ? w.sc->rz[k] / pqk : 0.0;
     double rm = 0.0;
-    SMRF_FOR_TILES(T, y, x, in) {
+    SMRF_FOR_TILE_BLOCKS(T, y0, x, in) {
         if (in) {
-            const int64_t i = y * nx + x;
-            if (unk[i]) {
-                w.u[i] += alpha * w.p[i];
-                const double r = w.r[i] - alpha * w.q[i];
-                w.r[i] = r;
-                w.lev[0].b[i] = (float)r;
-                rm = fmax(rm, fabs(r));
+            uint8_t mk[kRows];
+            double pv[kRows], qv[kRows], uv[kRows], rv[kRows];
+            const int64_t i0 = y0 * nx + x;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) mk[r] = (y0 + r < ny) ? unk[i0 + r * nx] : 0;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                if (mk[r]) {
+                    pv[r] = w.p[i0 + r * nx]; qv[r] = w.q[i0 + r * nx];
+                    uv[r] = w.u[i0 + r * nx]; rv[r] = w.r[i0 + r * nx];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                if (mk[r]) {
+                    const double rn = rv[r] - alpha * qv[r];
+                    w.u[i0 + r * nx] = uv[r] + alpha * pv[r];
+                    w.r[i0 + r * nx] = rn;
+                    w.lev[0].b[i0 + r * nx] = (float)rn;
+                    rm = fmax(rm, fabs(rn));
+                }
             }
         }
     }
@@ -403,53 +499,180 @@ __global__ void __launch_bounds__(kBlock) prolong_kernel(float* __restrict__ x, 
     }
 }
 
+// ---- fused legs of the V-cycle: each level is two launches and two passes over its vectors ----
+// A CTA owns a 28 x 60 tile; everything a sweep needs from neighbours is recomputed in a
+// two-cell halo held in shared memory (temporal blocking of the two Jacobi sweeps).  The
+// halo'd tile is 32 x 64 so that local indices are shifts and masks; the in-grid test, the
+// mask and 1/degree are evaluated once per element while loading.
+constexpr int kTY = 28, kTX = 60;
+constexpr int kHY = 32, kHX = 64;
+
+struct TileBuf {
+    float b[kHY][kHX];
+    float s0[kHY][kHX];
+    float s1[kHY][kHX];
+    float dinv[kHY][kHX];   // omega / degree on unknown cells, 0 elsewhere (which also zeroes the iterate there)
+    float deg[kHY][kHX];
+};
+
+// x + omega (b - A x) / deg, with x == 0 off the unknown set (dinv == 0 there keeps it so)
+__device__ __forceinline__ float jacobi(const float (*x)[kHX], const TileBuf& t, int ly, int lx) {
+    const float xi = x[ly][lx];
+    const float s = x[ly - 1][lx] + x[ly + 1][lx] + x[ly][lx - 1] + x[ly][lx + 1];
+    return t.dinv[ly][lx] == 0.f ? 0.f : xi + t.dinv[ly][lx] * (t.b[ly][lx] - (t.deg[ly][lx] * xi - s));
+}
+
+// loads b (and optionally an iterate) of the halo'd tile; returns nothing, fills t.b, t.dinv, t.deg, t.s0
+template <bool UP>
+__device__ __forceinline__ void load_tile(TileBuf& t, const float* __restrict__ b, const uint8_t* __restrict__ m,
+                                          const float* __restrict__ x, const float* __restrict__ xc, int64_t y0,
+                                          int64_t x0, int64_t ny, int64_t nx, int64_t cx, int above, int below) {
+#pragma unroll
+    for (int e = 0; e < kHY * kHX / kBlock; ++e) {
+        const int i = threadIdx.x + e * kBlock;
+        const int ly = i >> 6, lx = i & 63;
+        const int64_t y = y0 + ly - 2, xx = x0 + lx - 2;
+        const bool in = y >= 0 && y < ny && xx >= 0 && xx < nx;
+        const int64_t g = y * nx + xx;
+        const bool mm = in && m[g];
+        float bb = 0.f, dv = 0.f, dg = 0.f, s = 0.f;
+        if (mm) {
+            bb = b[g];
+            const int d = degree(y, xx, ny, nx, above, below);
+            dg = (float)d;
+            dv = kOmega / (float)(d > 0 ? d : 1);
+            if (UP) s = x[g] + xc[(y >> 1) * cx + (xx >> 1)];
+            else s = dv * bb;                      // first sweep from the zero vector
+        }
+        t.b[ly][lx] = bb; t.dinv[ly][lx] = dv; t.deg[ly][lx] = dg; t.s0[ly][lx] = s;
+    }
+}
+
+// down leg: x = two damped-Jacobi sweeps from zero on A x = b;  bc = P^T (b - A x)
+__global__ void __launch_bounds__(kBlock) down_kernel(const float* __restrict__ b, const uint8_t* __restrict__ m,
+                                                      float* __restrict__ xout, const uint8_t* __restrict__ mc,
+                                                      float* __restrict__ bc, int64_t ny, int64_t nx, int64_t cy,
+                                                      int64_t cx, int above, int below) {
+    __shared__ TileBuf t;
+    const int64_t tiles_x = (nx + kTX - 1) / kTX, tiles = tiles_x * ((ny + kTY - 1) / kTY);
+    for (int64_t tile = tile_first(); tile < tiles; tile += tile_step()) {
+        const int64_t ty = tile / tiles_x;
+        const int64_t y0 = ty * kTY, x0 = (tile - ty * tiles_x) * kTX;
+        __syncthreads();
+        load_tile<false>(t, b, m, nullptr, nullptr, y0, x0, ny, nx, 0, above, below);
+        __syncthreads();
+        // second sweep on the tile plus one ring
+        for (int i = threadIdx.x; i < kHY * kHX; i += kBlock) {
+            const int ly = i >> 6, lx = i & 63;
+            if (ly >= 1 && ly <= kTY + 2 && lx >= 1 && lx <= kTX + 2) t.s1[ly][lx] = jacobi(t.s0, t, ly, lx);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kHY * kHX; i += kBlock) {
+            const int ly = i >> 6, lx = i & 63;
+            if (ly >= 2 && ly < kTY + 2 && lx >= 2 && lx < kTX + 2) {
+                const int64_t y = y0 + ly - 2, xx = x0 + lx - 2;
+                if (y < ny && xx < nx) xout[y * nx + xx] = t.s1[ly][lx];
+            }
+        }
+        // coarse right-hand side: 14 x 30 coarse cells per tile
+        for (int i = threadIdx.x; i < (kTY / 2) * 32; i += kBlock) {
+            const int cly = i >> 5, clx = i & 31;
+            const int64_t Y = y0 / 2 + cly, X = x0 / 2 + clx;
+            if (clx < kTX / 2 && Y < cy && X < cx) {
+                float acc = 0.f;
+                if (mc[Y * cx + X]) {
+#pragma unroll
+                    for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+                        for (int c2 = 0; c2 < 2; ++c2) {
+                            const int ly = 2 * cly + a2 + 2, lx = 2 * clx + c2 + 2;
+                            if (t.dinv[ly][lx] != 0.f) {
+                                const float sum = t.s1[ly - 1][lx] + t.s1[ly + 1][lx] + t.s1[ly][lx - 1] + t.s1[ly][lx + 1];
+                                acc += t.b[ly][lx] - (t.deg[ly][lx] * t.s1[ly][lx] - sum);
+                            }
+                        }
+                }
+                bc[Y * cx + X] = acc;
+            }
+        }
+    }
+}
+
+// up leg: x += P xc, then two damped-Jacobi sweeps; written to `xout` (another buffer: tiles read
+// each other's halo of x)
+__global__ void __launch_bounds__(kBlock) up_kernel(const float* __restrict__ x, const float* __restrict__ xc,
+                                                    const float* __restrict__ b, const uint8_t* __restrict__ m,
+                                                    float* __restrict__ xout, int64_t ny, int64_t nx, int64_t cx,
+                                                    int above, int below) {
+    __shared__ TileBuf t;
+    const int64_t tiles_x = (nx + kTX - 1) / kTX, tiles = tiles_x * ((ny + kTY - 1) / kTY);
+    for (int64_t tile = tile_first(); tile < tiles; tile += tile_step()) {
+        const int64_t ty = tile / tiles_x;
+        const int64_t y0 = ty * kTY, x0 = (tile - ty * tiles_x) * kTX;
+        __syncthreads();
+        load_tile<true>(t, b, m, x, xc, y0, x0, ny, nx, cx, above, below);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kHY * kHX; i += kBlock) {
+            const int ly = i >> 6, lx = i & 63;
+            if (ly >= 1 && ly <= kTY + 2 && lx >= 1 && lx <= kTX + 2) t.s1[ly][lx] = jacobi(t.s0, t, ly, lx);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kHY * kHX; i += kBlock) {
+            const int ly = i >> 6, lx = i & 63;
+            if (ly >= 2 && ly < kTY + 2 && lx >= 2 && lx < kTX + 2) {
+                const int64_t y = y0 + ly - 2, xx = x0 + lx - 2;
+                if (y < ny && xx < nx) xout[y * nx + xx] = jacobi(t.s1, t, ly, lx);
+            }
+        }
+    }
+}
+
+static inline int fused_grid(int64_t ny, int64_t nx) {
+    int64_t t = ((nx + kTX - 1) / kTX) * ((ny + kTY - 1) / kTY);
+    int64_t cap = (int64_t)num_sms() * 8;
+    if (t > cap) t = cap;
+    if (t < 1) t = 1;
+    return (int)t;
+}
+
 static inline int tile_grid(int64_t ny, int64_t nx) {
-    int64_t t = ny * ((nx + kBlock - 1) / kBlock);
+    int64_t t = ((ny + kRows - 1) / kRows) * ((nx + kBlock - 1) / kBlock);
     int64_t cap = (int64_t)num_sms() * 16;
     if (t > cap) t = cap;
     if (t < 1) t = 1;
     return (int)t;
 }
 
-// z = M^-1 b0: one V(2,2) cycle; returns the buffer holding the level-0 result
+// z = M^-1 b0: one V(2,2) cycle; the level-0 result is left in lev[0].y
 static const float* vcycle(Ws& w, cudaStream_t st, int* launches) {
     const int L = w.nlev;
-    float* cur[kMaxLevels];
     int n = 0;
-    for (int l = 0; l < L; ++l) {
-        Level& v = w.lev[l];
+    for (int l = 0; l + 1 < L; ++l) {
+        Level &v = w.lev[l], &c = w.lev[l + 1];
+        down_kernel<<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.b, v.m, v.x, c.m, c.b, v.ny, v.nx, c.ny, c.nx,
+                                                               w.has_above, w.has_below);
+        ++n;
+    }
+    {   // coarsest level: a fixed number of sweeps (a symmetric operator, like the rest of the cycle)
+        Level& v = w.lev[L - 1];
         const int g = tile_grid(v.ny, v.nx);
         smooth_kernel<true><<<g, kBlock, 0, st>>>(nullptr, v.x, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
-        ++n;
-        if (l == L - 1) {
-            float *a = v.x, *b = v.y;
-            for (int s = 1; s < kCoarsestSweeps; ++s) {
-                smooth_kernel<false><<<g, kBlock, 0, st>>>(a, b, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
-                float* t = a; a = b; b = t;
-                ++n;
-            }
-            cur[l] = a;
-        } else {
-            smooth_kernel<false><<<g, kBlock, 0, st>>>(v.x, v.y, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
-            cur[l] = v.y;
-            Level& c = w.lev[l + 1];
-            restrict_kernel<<<tile_grid(c.ny, c.nx), kBlock, 0, st>>>(cur[l], v.b, c.m, c.b, v.ny, v.nx, c.ny, c.nx, w.has_above, w.has_below);
-            n += 2;
+        float *a = v.x, *b = v.y;
+        for (int s2 = 1; s2 < kCoarsestSweeps; ++s2) {
+            smooth_kernel<false><<<g, kBlock, 0, st>>>(a, b, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
+            float* t = a; a = b; b = t;
         }
+        n += kCoarsestSweeps;
+        // kCoarsestSweeps is even: the result sits in v.y, as on every other level
     }
     for (int l = L - 2; l >= 0; --l) {
-        Level& v = w.lev[l];
-        const int g = tile_grid(v.ny, v.nx);
-        float* a = cur[l];
-        float* b = (a == v.x) ? v.y : v.x;
-        prolong_kernel<<<g, kBlock, 0, st>>>(a, cur[l + 1], v.m, v.ny, v.nx, w.lev[l + 1].nx);
-        smooth_kernel<false><<<g, kBlock, 0, st>>>(a, b, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
-        smooth_kernel<false><<<g, kBlock, 0, st>>>(b, a, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
-        cur[l] = a;
-        n += 3;
+        Level &v = w.lev[l], &c = w.lev[l + 1];
+        up_kernel<<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.x, c.y, v.b, v.m, v.y, v.ny, v.nx, c.nx, w.has_above,
+                                                             w.has_below);
+        ++n;
     }
     *launches += n;
-    return cur[0];
+    return w.lev[0].y;
 }
 
 }  // namespace inpaint
@@ -530,8 +753,8 @@ int smrf_inpaint_setup(const void* grid, int64_t ny, int64_t nx, int dtype, void
 }
 
 int smrf_inpaint_start(const void* grid, int64_t ny, int64_t nx, int dtype, void* workspace, size_t workspace_bytes,
-                       int has_above, int has_below, double guess, int phase, const double* u_above,
-                       const double* u_below, void* stream) {
+                       int has_above, int has_below, double guess, const void* guess_grid, int phase,
+                       const double* u_above, const double* u_below, void* stream) {
     SMRF_CHECK_ARG(grid, "null grid");
     SMRF_CHECK_ARG(dtype == SMRF_F32 || dtype == SMRF_F64, "bad dtype");
     SMRF_CHECK_ARG(phase == 0 || phase == 1, "bad phase");
@@ -547,8 +770,8 @@ int smrf_inpaint_start(const void* grid, int64_t ny, int64_t nx, int dtype, void
         unsigned long long one = 1;
         SMRF_CUDA(cudaMemcpyAsync(&w.sc->sum_known, &g, 8, cudaMemcpyHostToDevice, st));
         SMRF_CUDA(cudaMemcpyAsync(&w.sc->n_known, &one, 8, cudaMemcpyHostToDevice, st));
-        if (dtype == SMRF_F32) init_u_kernel<float><<<g1_for(n), kBlock, 0, st>>>((const float*)grid, w.lev[0].m, w.u, n, w.sc);
-        else init_u_kernel<double><<<g1_for(n), kBlock, 0, st>>>((const double*)grid, w.lev[0].m, w.u, n, w.sc);
+        if (dtype == SMRF_F32) init_u_kernel<float><<<g1_for(n), kBlock, 0, st>>>((const float*)grid, w.lev[0].m, w.u, n, w.sc, (const float*)guess_grid);
+        else init_u_kernel<double><<<g1_for(n), kBlock, 0, st>>>((const double*)grid, w.lev[0].m, w.u, n, w.sc, (const double*)guess_grid);
     } else {
         SMRF_CHECK_ARG((!has_above || u_above) && (!has_below || u_below), "missing halo row of u");
         residual0_kernel<<<tile_grid(ny, nx), kBlock, 0, st>>>(w, ny, nx, u_above, u_below);
@@ -615,7 +838,7 @@ int smrf_inpaint_finish(void* grid, int64_t ny, int64_t nx, int dtype, void* wor
     return 0;
 }
 
-int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown, void* workspace,
+int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown, const void* guess, void* workspace,
                  size_t workspace_bytes, double tol, int max_iter, double* info_host, void* stream) {
     SMRF_CHECK_ARG(grid && workspace, "null pointer");
     SMRF_CHECK_ARG(ny > 0 && nx > 0, "empty grid");
@@ -637,8 +860,8 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
     double rmax = 0.0;
     if (n_unknown > 0) {
         const double mean = stats.nk ? stats.sum / (double)stats.nk : 0.0;
-        if (int rc = smrf_inpaint_start(grid, ny, nx, dtype, workspace, workspace_bytes, 0, 0, mean, 0, nullptr, nullptr, stream)) return rc;
-        if (int rc = smrf_inpaint_start(grid, ny, nx, dtype, workspace, workspace_bytes, 0, 0, mean, 1, nullptr, nullptr, stream)) return rc;
+        if (int rc = smrf_inpaint_start(grid, ny, nx, dtype, workspace, workspace_bytes, 0, 0, mean, guess, 0, nullptr, nullptr, stream)) return rc;
+        if (int rc = smrf_inpaint_start(grid, ny, nx, dtype, workspace, workspace_bytes, 0, 0, mean, nullptr, 1, nullptr, nullptr, stream)) return rc;
         unsigned long long bits = 0;
         SMRF_CUDA(cudaMemcpyAsync(&bits, &w.sc->rmax[0], 8, cudaMemcpyDeviceToHost, st));
         SMRF_CUDA(cudaStreamSynchronize(st));

@@ -90,7 +90,7 @@ def _api():
     return _lib, api
 
 
-def _inpaint_band(lib, band, ws, tol, group, max_iter=4000):
+def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None):
     """Distributed multigrid-preconditioned CG on a row band (see module docstring)."""
     _lib, api = _api()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -121,9 +121,9 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000):
         return info, ws
     mean = s_known / n_known if n_known else 0.0
     m_above, m_below = exchange_halo(m, 1, group)
-    _lib.check(lib.smrf_inpaint_start(api._ptr(band), ny, nx, code, wp, wn, ha, hb, mean, 0, None, None, st()), 'start0')
+    _lib.check(lib.smrf_inpaint_start(api._ptr(band), ny, nx, code, wp, wn, ha, hb, mean, api._ptr(guess), 0, None, None, st()), 'start0')
     u_above, u_below = exchange_halo(u, 1, group)
-    _lib.check(lib.smrf_inpaint_start(api._ptr(band), ny, nx, code, wp, wn, ha, hb, mean, 1, api._ptr(u_above),
+    _lib.check(lib.smrf_inpaint_start(api._ptr(band), ny, nx, code, wp, wn, ha, hb, mean, None, 1, api._ptr(u_above),
                                       api._ptr(u_below), st()), 'start1')
 
     def residual(k):
@@ -158,28 +158,70 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000):
     return info, ws
 
 
+def plan_window_chunks(windows, rows, world):
+    """Group consecutive windows so that one halo exchange serves a whole group: a group
+    whose radii are w_1..w_k needs sum(2 w_i) rows from each neighbour (every window eats 2w
+    rows of validity at an interior band edge).  Groups are closed when that sum would exceed
+    what a neighbour can serve (its own rows) or ~1/16 of the band (redundant halo work)."""
+    if world == 1:
+        return [list(range(len(windows)))] if len(windows) else []
+    limit = max(2 * int(max(windows)), min(rows, max(64, rows // 16)))
+    chunks, cur, acc = [], [], 0
+    for i, w in enumerate(windows):
+        need = 2 * int(w)
+        if cur and acc + need > limit:
+            chunks.append(cur)
+            cur, acc = [], 0
+        cur.append(i)
+        acc += need
+    if cur:
+        chunks.append(cur)
+    return chunks
+
+
 def _open_windows_band(lib, band, windows, thresholds, mask, when, negate, group):
-    """Progressive opening of a row band: 2w halo rows per window from each neighbour."""
+    """Progressive opening of a row band.  Windows are processed in groups; before a group the
+    band receives sum(2w) rows of the current surface from each neighbour, then every window
+    of the group runs on the extended buffer, its valid row range shrinking by 2w at each
+    interior edge (the halo rows are recomputed redundantly instead of being re-exchanged)."""
     _lib, api = _api()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
     rows, nx = band.shape
     code, st = api._code(band.dtype), api._stream
     cur = band
     last = None
-    for i, w in enumerate(windows):
-        w = int(w)
-        buf, top = with_halo(cur, 2 * w, group)
-        out = torch.empty_like(buf)
-        tmp = torch.empty_like(buf)
-        # the kernel indexes mask/when with the same rows as `buf`: shift the base so that
-        # buffer row `top` is band row 0 (only rows [top, top + rows) are ever touched)
-        mptr = C.c_void_p(mask.data_ptr() - top * nx)
-        wptr = C.c_void_p(when.data_ptr() - top * nx) if when is not None else None
-        _lib.check(lib.smrf_open_window(api._ptr(buf), api._ptr(out), api._ptr(tmp), mptr, wptr, buf.shape[0], nx,
-                                        code, w, float(thresholds[i]), i, int(negate), top, top + rows, st()),
-                   'smrf_open_window')
-        last = out[top:top + rows]
-        if len(windows) > 1:          # neilpy.py:1675-1676
-            cur = last
+    min_rows = torch.tensor([rows], dtype=torch.int64, device=band.device)
+    if world > 1:
+        dist.all_reduce(min_rows, op=dist.ReduceOp.MIN, group=group)
+    for chunk in plan_window_chunks([int(w) for w in windows], int(min_rows.item()), world):
+        H = sum(2 * int(windows[i]) for i in chunk)
+        buf, top = with_halo(cur, H, group)
+        nb = buf.shape[0]
+        bot = nb - top - rows
+        # chunk-local mask planes shaped like the buffer (the kernel flags halo rows too)
+        mbuf = torch.zeros((nb, nx), dtype=torch.uint8, device=band.device)
+        mbuf[top:top + rows] = mask
+        wbuf = None
+        if when is not None:
+            wbuf = torch.zeros((nb, nx), dtype=torch.uint8, device=band.device)
+            wbuf[top:top + rows] = when
+        a, b, tmp = buf, torch.empty_like(buf), torch.empty_like(buf)
+        v0, v1 = 0, nb
+        for i in chunk:
+            w = int(windows[i])
+            v0 = v0 + 2 * w if top else 0
+            v1 = v1 - 2 * w if bot else nb
+            _lib.check(lib.smrf_open_window(api._ptr(a), api._ptr(b), api._ptr(tmp), api._ptr(mbuf), api._ptr(wbuf),
+                                            nb, nx, code, w, float(thresholds[i]), i, int(negate), v0, v1, st()),
+                       'smrf_open_window')
+            last = b[top:top + rows]
+            if len(windows) > 1:          # neilpy.py:1675-1676: last_surface advances only then
+                a, b = b, a
+        mask.copy_(mbuf[top:top + rows])
+        if when is not None:
+            when.copy_(wbuf[top:top + rows])
+        if len(windows) > 1:
+            cur = a[top:top + rows]
     return last
 
 
@@ -197,8 +239,18 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     lib = _lib.load()
     dev = api._device()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    import os, time
+    timing = {} if os.environ.get('SMRF_TIMING') else None
+    t_last = [time.perf_counter()]
+
+    def mark(name):
+        if timing is not None:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            timing[name] = round((now - t_last[0]) * 1e3, 3)
+            t_last[0] = now
     windows = api._windows(windows)
-    tol = api.INPAINT_TOL if inpaint_tol is None else inpaint_tol
+    tol = api.SMRF_INPAINT_TOL if inpaint_tol is None else inpaint_tol
     if isinstance(points, (tuple, list)):
         pts = api._Points(points[0], points[1], points[2], dev)
     else:
@@ -222,6 +274,7 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     (xmin, ymin), (xmax, ymax) = [float(v) for v in lo.cpu()], [float(v) for v in hi.cpu()]
     xedges, yedges = api._edges(xmin, xmax, ymin, ymax, cellsize)
     nx, ny = len(xedges) - 1, len(yedges) - 1
+    mark('extent')
     wmax = int(windows.max()) if len(windows) else 1
     check_partition(ny, world, max(2 * wmax, SPLINE_HALO))
     t = api._make_transform(xedges[0], yedges[0], cellsize)
@@ -248,21 +301,28 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     empty = torch.empty((rows, nx), dtype=torch.uint8, device=dev)
     _lib.check(lib.smrf_bin_mark_empty(api._ptr(Zmin), api._ptr(empty), rows, nx, code, _lib.BIN_MIN, st()),
                'smrf_bin_mark_empty')
+    mark('binning')
 
     # ---- inpaint, low outliers, progressive filter, punch, inpaint
     info1, ws = _inpaint_band(lib, Zmin, None, tol, group)
+    mark('inpaint1')
     low = torch.zeros((rows, nx), dtype=torch.uint8, device=dev)
     one = np.array([1])
     _open_windows_band(lib, Zmin, one, low_filter_slope * (one * cellsize), low, None, 1, group)
     obj = torch.zeros((rows, nx), dtype=torch.uint8, device=dev)
+    opened = None
     if len(windows):
-        _open_windows_band(lib, Zmin, windows, slope_threshold * (windows * cellsize), obj, None, 0, group)
+        opened = _open_windows_band(lib, Zmin, windows, slope_threshold * (windows * cellsize), obj, None, 0, group)
+        opened = opened.contiguous()
+    mark('opening')
     object_cells = torch.empty((rows, nx), dtype=torch.uint8, device=dev)
     _lib.check(lib.smrf_merge_punch(api._ptr(Zmin), api._ptr(empty), api._ptr(low), api._ptr(obj),
                                     api._ptr(object_cells), rows, nx, code, st()), 'smrf_merge_punch')
     Zpro = Zmin
-    info2, ws = _inpaint_band(lib, Zpro, ws, tol, group)
+    info2, ws = _inpaint_band(lib, Zpro, ws, tol, group, guess=opened)
+    del opened
     del ws
+    mark('inpaint2')
 
     # ---- slope (1 halo row), spline coefficients (SPLINE_HALO rows), all-gather
     buf, top = with_halo(Zpro, 1, group)
@@ -291,12 +351,14 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
 
     coef_z = coefficients(Zpro)
     coef_s = coefficients(S)
+    mark('slope+spline')
     is_obj = torch.empty(pts.n, dtype=torch.uint8, device=dev)
     _lib.check(lib.smrf_classify(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, api._ptr(coef_z),
                                  api._ptr(coef_s), ny, nx, code, float(elevation_threshold), float(elevation_scaler),
                                  api._ptr(is_obj), None, None, None, None, st()), 'smrf_classify')
+    mark('classify')
     res = {'t': t, 'shape': (ny, nx), 'rows': (r0, r1), 'is_object_point': is_obj.view(torch.bool),
-           'info': {'inpaint1': info1, 'inpaint2': info2}}
+           'info': {'inpaint1': info1, 'inpaint2': info2, 'timing_ms': timing}}
     if gather and world > 1:
         def full(band, fill):
             mine = torch.full((per, nx), fill, dtype=band.dtype, device=dev)

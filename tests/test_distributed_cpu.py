@@ -24,6 +24,16 @@ def test_band_bounds_cover_the_grid():
     D.check_partition(5001, 8, 80)
 
 
+def test_window_chunks():
+    w = list(range(1, 19))
+    assert D.plan_window_chunks(w, 5001, 1) == [list(range(18))]
+    ch = D.plan_window_chunks(w, 5001, 2)
+    assert sum(ch, []) == list(range(18)) and len(ch) <= 3
+    for c in ch:
+        assert sum(2 * w[i] for i in c) <= max(36, 5001 // 16)
+    assert all(len(c) >= 1 for c in D.plan_window_chunks(list(range(1, 37)), 4096, 8))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
@@ -75,6 +85,33 @@ def _worker(rank, world, port, ny, nx, out):
             mask |= (cur.numpy() - this) > thr[i]
             cur = torch.from_numpy(np.ascontiguousarray(this))
         ok &= bool(np.array_equal(mask, ref_mask[r0:r1]))
+        # grouped form: one exchange of sum(2w) rows per group, validity shrinking by 2w per window
+        def open_ignore_oob(b, w):
+            er = O.ndi.grey_erosion(np.pad(b, w, constant_values=np.inf), footprint=O.disk(w), mode='constant', cval=np.inf)[w:-w, w:-w]
+            return O.ndi.grey_dilation(np.pad(er, w, constant_values=-np.inf), footprint=O.disk(w), mode='constant', cval=-np.inf)[w:-w, w:-w]
+        cur = band
+        mask2 = np.zeros((r1 - r0, nx), dtype=bool)
+        chunks = D.plan_window_chunks([int(w) for w in windows], 40, world)     # forces two groups
+        ok &= len(chunks) >= 2 and sorted(sum(chunks, [])) == list(range(len(windows)))
+        for chunk in chunks:
+            H = sum(2 * int(windows[i]) for i in chunk)
+            buf, top = D.with_halo(cur, H)
+            b = buf.numpy().copy()
+            bot = b.shape[0] - top - (r1 - r0)
+            v0, v1 = 0, b.shape[0]
+            for i in chunk:
+                w = int(windows[i])
+                v0 = v0 + 2 * w if top else 0
+                v1 = v1 - 2 * w if bot else b.shape[0]
+                this = open_ignore_oob(b, w)          # wrong outside [v0, v1) at interior edges, by construction
+                new = (b - this) > thr[i]
+                mask2 |= new[top:top + (r1 - r0)]
+                garbage = np.full_like(b, 1e9)        # rows outside the valid range must never matter
+                garbage[v0:v1] = this[v0:v1]
+                b = garbage
+            ok &= v0 <= top and v1 >= top + (r1 - r0)
+            cur = torch.from_numpy(np.ascontiguousarray(b[top:top + (r1 - r0)]))
+        ok &= bool(np.array_equal(mask2, ref_mask[r0:r1]))
         flag = torch.tensor([1 if ok else 0])
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
@@ -88,7 +125,7 @@ def test_band_halo_rule_with_two_gloo_ranks():
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 80, 45, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 160, 45, q)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
