@@ -319,7 +319,7 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     _lib.check(lib.smrf_merge_punch(api._ptr(Zmin), api._ptr(empty), api._ptr(low), api._ptr(obj),
                                     api._ptr(object_cells), rows, nx, code, st()), 'smrf_merge_punch')
     Zpro = Zmin
-    info2, ws = _inpaint_band(lib, Zpro, ws, tol, group, guess=opened)
+    info2, ws = _inpaint_band(lib, Zpro, ws, tol, group, guess=None if os.environ.get('SMRF_NO_GUESS') else opened)
     del opened
     del ws
     mark('inpaint2')

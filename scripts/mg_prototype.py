@@ -78,7 +78,7 @@ def pcg(A_grid, tol=1e-9, precond='mg', maxit=3000, **kw):
         p = z + (rz2 / rz) * p; rz = rz2; it += 1
     return u, it
 
-if __name__ == '__main__':
+if __name__ == '__main__' and len(sys.argv) == 1:
     x, y, z, _ = O.synth_cloud(500000, 500.0, 500.0, seed=0)
     st = {}
     O.smrf(x, y, z, 1, 18, .15, .5, 1.25, stages=st)
@@ -91,3 +91,47 @@ if __name__ == '__main__':
                 for scale in (1.0, 2.0):
                     t0 = time.time(); u, it = pcg(G, precond='mg', mode=mode, nu=nu, scale=scale)
                     print(name, 'mg', mode, 'nu', nu, 'scale', scale, 'iters', it, 'err', np.abs(u - ex).max(), '%.1fs' % (time.time() - t0))
+
+
+def band_experiment():
+    """block-Jacobi over two row bands, each with its own V-cycle (what distributed.py does)"""
+    x, y, z, _ = O.synth_cloud(500000, 500.0, 500.0, seed=0)
+    st = {}
+    O.smrf(x, y, z, 1, 18, .15, .5, 1.25, stages=st)
+    G = st['Zpro_punched']
+    unk = np.isnan(G)
+    deg = deg_of(unk.shape)
+    ny = G.shape[0]; h = ny // 2
+
+    class BandMG(MG):
+        def __init__(self, unk, above, below, **kw):
+            super().__init__(unk, **kw)
+            lev = []
+            for (u, d) in self.levels:
+                d = d.copy()
+                if above: d[0, :] += 1
+                if below: d[-1, :] += 1
+                lev.append((u, d))
+            self.levels = lev
+    top, bot = BandMG(unk[:h], False, True, nu=2), BandMG(unk[h:], True, False, nu=2)
+    full = MG(unk, nu=2)
+
+    def run(M, tol=1e-7):
+        u = np.where(unk, np.nanmean(G), G)
+        s = np.zeros_like(u)
+        s[1:, :] += u[:-1, :]; s[:-1, :] += u[1:, :]; s[:, 1:] += u[:, :-1]; s[:, :-1] += u[:, 1:]
+        r = np.where(unk, s - deg * u, 0.0)
+        zz = M(r); p = zz.copy(); rz = (r * zz).sum(); it = 0
+        while np.abs(r).max() > tol and it < 500:
+            q = applyA(p, unk, deg)
+            a = rz / (p * q).sum()
+            u += a * p; r -= a * q
+            zz = M(r); rz2 = (r * zz).sum()
+            p = zz + (rz2 / rz) * p; rz = rz2; it += 1
+        return it
+    print('global V-cycle      :', run(lambda r: full.vcycle(0, r)))
+    print('two-band block V    :', run(lambda r: np.vstack([top.vcycle(0, r[:h]), bot.vcycle(0, r[h:])])))
+
+
+if len(sys.argv) > 1 and sys.argv[1] == 'bands':
+    band_experiment()
