@@ -519,32 +519,78 @@ struct TileBuf {
 __device__ __forceinline__ float jacobi(const float (*x)[kHX], const TileBuf& t, int ly, int lx) {
     const float xi = x[ly][lx];
     const float s = x[ly - 1][lx] + x[ly + 1][lx] + x[ly][lx - 1] + x[ly][lx + 1];
-    return t.dinv[ly][lx] == 0.f ? 0.f : xi + t.dinv[ly][lx] * (t.b[ly][lx] - (t.deg[ly][lx] * xi - s));
+    const float dv = t.dinv[ly][lx];
+    return dv == 0.f ? 0.f : xi + dv * (t.b[ly][lx] - (t.deg[ly][lx] * xi - s));
 }
 
-// loads b (and optionally an iterate) of the halo'd tile; returns nothing, fills t.b, t.dinv, t.deg, t.s0
+// Thread mapping of the fused legs: thread t owns column lx = t & 63 of the halo'd tile and the
+// rows ly = (t >> 6) + 4 e, e = 0..7, so everything that depends on the column only (in-grid
+// test, horizontal part of the degree, base address) is computed once per tile.
+struct TilePos {
+    int lx, lyb;        // local column, first local row
+    int y_first;        // grid row of local row lyb
+    bool col_ok;        // column inside the grid
+    int dxh;            // in-grid horizontal neighbours
+    int64_t g0;         // flat index of (y_first, column)
+};
+__device__ __forceinline__ TilePos tile_pos(int64_t y0, int64_t x0, int64_t nx) {
+    TilePos p;
+    p.lx = threadIdx.x & 63;
+    p.lyb = threadIdx.x >> 6;
+    const int64_t xx = x0 + p.lx - 2;
+    p.y_first = (int)(y0 - 2 + p.lyb);
+    p.col_ok = xx >= 0 && xx < nx;
+    p.dxh = (xx > 0) + (xx + 1 < nx);
+    p.g0 = (int64_t)p.y_first * nx + xx;
+    return p;
+}
+
+// loads b (and, on the way up, the iterate plus the coarse correction) of the halo'd tile;
+// fills t.b, t.dinv, t.deg, t.s0
 template <bool UP>
-__device__ __forceinline__ void load_tile(TileBuf& t, const float* __restrict__ b, const uint8_t* __restrict__ m,
-                                          const float* __restrict__ x, const float* __restrict__ xc, int64_t y0,
-                                          int64_t x0, int64_t ny, int64_t nx, int64_t cx, int above, int below) {
+__device__ __forceinline__ void load_tile(TileBuf& t, const TilePos& p, const float* __restrict__ b,
+                                          const uint8_t* __restrict__ m, const float* __restrict__ x,
+                                          const float* __restrict__ xc, int ny, int64_t nx, int64_t cx, int above,
+                                          int below) {
+    uint8_t mm[8];
 #pragma unroll
-    for (int e = 0; e < kHY * kHX / kBlock; ++e) {
-        const int i = threadIdx.x + e * kBlock;
-        const int ly = i >> 6, lx = i & 63;
-        const int64_t y = y0 + ly - 2, xx = x0 + lx - 2;
-        const bool in = y >= 0 && y < ny && xx >= 0 && xx < nx;
-        const int64_t g = y * nx + xx;
-        const bool mm = in && m[g];
-        float bb = 0.f, dv = 0.f, dg = 0.f, s = 0.f;
-        if (mm) {
-            bb = b[g];
-            const int d = degree(y, xx, ny, nx, above, below);
-            dg = (float)d;
-            dv = kOmega / (float)(d > 0 ? d : 1);
-            if (UP) s = x[g] + xc[(y >> 1) * cx + (xx >> 1)];
-            else s = dv * bb;                      // first sweep from the zero vector
+    for (int e = 0; e < 8; ++e) {
+        const int y = p.y_first + 4 * e;
+        mm[e] = (p.col_ok && y >= 0 && y < ny) ? m[p.g0 + (int64_t)(4 * e) * nx] : 0;
+    }
+    float bb[8], xv[8], cv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int64_t g = p.g0 + (int64_t)(4 * e) * nx;
+        bb[e] = mm[e] ? b[g] : 0.f;
+        if (UP) {
+            const int y = p.y_first + 4 * e;
+            xv[e] = mm[e] ? x[g] : 0.f;
+            cv[e] = mm[e] ? xc[(int64_t)(y >> 1) * cx + ((g - (int64_t)y * nx) >> 1)] : 0.f;
         }
-        t.b[ly][lx] = bb; t.dinv[ly][lx] = dv; t.deg[ly][lx] = dg; t.s0[ly][lx] = s;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int y = p.y_first + 4 * e;
+        const int ly = p.lyb + 4 * e;
+        float dv = 0.f, dg = 0.f, s = 0.f;
+        if (mm[e]) {
+            const int d = p.dxh + ((y > 0) || above) + ((y + 1 < ny) || below);
+            dg = (float)d;
+            dv = kOmega * __frcp_rn((float)(d > 0 ? d : 1));
+            s = UP ? xv[e] + cv[e] : dv * bb[e];     // down: first sweep from the zero vector
+        }
+        t.b[ly][p.lx] = bb[e]; t.dinv[ly][p.lx] = dv; t.deg[ly][p.lx] = dg; t.s0[ly][p.lx] = s;
+    }
+}
+
+__device__ __forceinline__ void sweep_ring1(TileBuf& t, const TilePos& p) {   // s1 = jacobi(s0) on the tile plus one ring
+    if (p.lx >= 1 && p.lx <= kTX + 2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ly = p.lyb + 4 * e;
+            if (ly >= 1 && ly <= kTY + 2) t.s1[ly][p.lx] = jacobi(t.s0, t, ly, p.lx);
+        }
     }
 }
 
@@ -558,20 +604,17 @@ __global__ void __launch_bounds__(kBlock) down_kernel(const float* __restrict__ 
     for (int64_t tile = tile_first(); tile < tiles; tile += tile_step()) {
         const int64_t ty = tile / tiles_x;
         const int64_t y0 = ty * kTY, x0 = (tile - ty * tiles_x) * kTX;
+        const TilePos p = tile_pos(y0, x0, nx);
         __syncthreads();
-        load_tile<false>(t, b, m, nullptr, nullptr, y0, x0, ny, nx, 0, above, below);
+        load_tile<false>(t, p, b, m, nullptr, nullptr, (int)ny, nx, 0, above, below);
         __syncthreads();
-        // second sweep on the tile plus one ring
-        for (int i = threadIdx.x; i < kHY * kHX; i += kBlock) {
-            const int ly = i >> 6, lx = i & 63;
-            if (ly >= 1 && ly <= kTY + 2 && lx >= 1 && lx <= kTX + 2) t.s1[ly][lx] = jacobi(t.s0, t, ly, lx);
-        }
+        sweep_ring1(t, p);
         __syncthreads();
-        for (int i = threadIdx.x; i < kHY * kHX; i += kBlock) {
-            const int ly = i >> 6, lx = i & 63;
-            if (ly >= 2 && ly < kTY + 2 && lx >= 2 && lx < kTX + 2) {
-                const int64_t y = y0 + ly - 2, xx = x0 + lx - 2;
-                if (y < ny && xx < nx) xout[y * nx + xx] = t.s1[ly][lx];
+        if (p.col_ok && p.lx >= 2 && p.lx < kTX + 2) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ly = p.lyb + 4 * e, y = p.y_first + 4 * e;
+                if (ly >= 2 && ly < kTY + 2 && y < ny) xout[p.g0 + (int64_t)(4 * e) * nx] = t.s1[ly][p.lx];
             }
         }
         // coarse right-hand side: 14 x 30 coarse cells per tile
@@ -609,19 +652,17 @@ __global__ void __launch_bounds__(kBlock) up_kernel(const float* __restrict__ x,
     for (int64_t tile = tile_first(); tile < tiles; tile += tile_step()) {
         const int64_t ty = tile / tiles_x;
         const int64_t y0 = ty * kTY, x0 = (tile - ty * tiles_x) * kTX;
+        const TilePos p = tile_pos(y0, x0, nx);
         __syncthreads();
-        load_tile<true>(t, b, m, x, xc, y0, x0, ny, nx, cx, above, below);
+        load_tile<true>(t, p, b, m, x, xc, (int)ny, nx, cx, above, below);
         __syncthreads();
-        for (int i = threadIdx.x; i < kHY * kHX; i += kBlock) {
-            const int ly = i >> 6, lx = i & 63;
-            if (ly >= 1 && ly <= kTY + 2 && lx >= 1 && lx <= kTX + 2) t.s1[ly][lx] = jacobi(t.s0, t, ly, lx);
-        }
+        sweep_ring1(t, p);
         __syncthreads();
-        for (int i = threadIdx.x; i < kHY * kHX; i += kBlock) {
-            const int ly = i >> 6, lx = i & 63;
-            if (ly >= 2 && ly < kTY + 2 && lx >= 2 && lx < kTX + 2) {
-                const int64_t y = y0 + ly - 2, xx = x0 + lx - 2;
-                if (y < ny && xx < nx) xout[y * nx + xx] = jacobi(t.s1, t, ly, lx);
+        if (p.col_ok && p.lx >= 2 && p.lx < kTX + 2) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ly = p.lyb + 4 * e, y = p.y_first + 4 * e;
+                if (ly >= 2 && ly < kTY + 2 && y < ny) xout[p.g0 + (int64_t)(4 * e) * nx] = jacobi(t.s1, t, ly, p.lx);
             }
         }
     }
