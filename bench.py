@@ -125,7 +125,10 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    workers = max(1, min(os.cpu_count() or 1, 16))
+    # one single-threaded interpreter per core: the numeric back-ends must not oversubscribe
+    for v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMEXPR_NUM_THREADS'):
+        os.environ[v] = '1'
+    workers = max(1, min(len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1), 32))
     n = args.ref_points
     ctx = mp.get_context('spawn')
     times = []

@@ -135,3 +135,19 @@ def band_experiment():
 
 if len(sys.argv) > 1 and sys.argv[1] == 'bands':
     band_experiment()
+
+
+def nu_experiment():
+    x, y, z, _ = O.synth_cloud(500000, 500.0, 500.0, seed=0)
+    st = {}
+    O.smrf(x, y, z, 1, 18, .15, .5, 1.25, stages=st)
+    for name in ('Zmin_binned', 'Zpro_punched'):
+        G = st[name]
+        for nu in (1, 2, 3, 4):
+            for om in (0.8, 0.9, 1.0):
+                u, it = pcg(G, tol=1e-7, precond='mg', mode='all', nu=nu, omega=om)
+                print(name, 'nu', nu, 'omega', om, 'iters', it, 'sweep-iters', it * nu)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == 'nu':
+    nu_experiment()
