@@ -116,7 +116,7 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
  *   setup  : NaN mask + multigrid hierarchy of the band; statistics of the known cells
  *   start  : phase 0: u = known value, else guess_grid (if given), else `guess`;  phase 1: r = b - A u with the
  *            neighbours' boundary rows of u (u_above / u_below, nx doubles each)
- *   step   : phase 0: z = M^-1 r (band-local V-cycle), rz[k] += r.z
+ *   step   : phase 0: z = M^-1 r (band-local V-cycle), rz[k] += r.z   (phase 20: rz only, z = z_ext)
  *            phase 1: p = z + (rz[k]/rz[k-1]) p
  *            phase 2: q = A p with the neighbours' boundary rows of p and of the NaN mask,
  *                     pq[k] += p.q
@@ -135,8 +135,28 @@ int smrf_inpaint_start(const void* grid, int64_t ny, int64_t nx, int dtype, void
                        const void* guess_grid, int phase, const double* u_above, const double* u_below,
                        void* stream);
 int smrf_inpaint_step(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, int has_above,
-                      int has_below, int k, int phase, const double* p_above, const double* p_below,
-                      const uint8_t* m_above, const uint8_t* m_below, void* stream);
+                      int has_below, int k, int phase, const float* z_ext, const double* p_above,
+                      const double* p_below, const uint8_t* m_above, const uint8_t* m_below, void* stream);
+/* Preconditioning a row band with the GLOBAL V-cycle.  A band-local cycle (any closure at the band
+ * edge) mistreats every error mode that is smooth across the edge and costs ~60 % more CG
+ * iterations; instead the caller (neilpy_b200/distributed.py)
+ *   - keeps a second hierarchy for the band extended by G ghost rows per side (masks exchanged
+ *     once; G >= the cycle's dependency radius of the band-local levels, 35 rows for 3 levels),
+ *   - per iteration exchanges G rows of the level-0 right-hand side, runs the down legs of levels
+ *     [0, split) on the extended band (smrf_mg_cycle_part, part 0), all-gathers the owned rows of
+ *     the level-`split` right-hand side into a hierarchy of the global coarse grid that every
+ *     rank holds (smrf_mg_setup_mask once, smrf_mg_vcycle per iteration), copies the rows of the
+ *     global coarse correction that its extended band covers back, and runs the up legs (part 2);
+ *   - hands the owned rows of the result to step phase 20 (rz) and phase 1 (p) as z_ext.
+ * On the owned rows this equals the single-GPU V-cycle, so the iteration count does not depend
+ * on the number of bands.  part 1 = the cycle from level `split` to the coarsest and back.
+ * smrf_mg_level_layout: {ny_l, nx_l, byte offsets of mask, x, y (result), b (rhs)} of a level. */
+int smrf_mg_level_layout(int64_t ny, int64_t nx, int level, int64_t* out6_host);
+int smrf_mg_setup_mask(const uint8_t* mask, int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes,
+                       void* stream);
+int smrf_mg_cycle_part(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, int has_above,
+                       int has_below, int split, int part, void* stream);
+int smrf_mg_vcycle(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, void* stream);
 int smrf_inpaint_finish(void* grid, int64_t ny, int64_t nx, int dtype, void* workspace,
                         size_t workspace_bytes, void* stream);
 

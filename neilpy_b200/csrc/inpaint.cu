@@ -684,35 +684,61 @@ static inline int tile_grid(int64_t ny, int64_t nx) {
     return (int)t;
 }
 
-// z = M^-1 b0: one V(2,2) cycle; the level-0 result is left in lev[0].y
-static const float* vcycle(Ws& w, cudaStream_t st, int* launches) {
+// Parts of one V(2,2) cycle.  part 0: down legs of levels [0, split) (leaves lev[split].b);
+// part 1: everything from level `split` down to the coarsest and back (leaves lev[split].y);
+// part 2: up legs of levels split-1 .. 0 (leaves lev[0].y).  split == 0 with all three parts
+// is the whole cycle.  The row-band solver runs parts 0 and 2 on its band and part 1 on a
+// hierarchy of the global coarse grid that every rank holds (neilpy_b200/distributed.py).
+static void vcycle_part(Ws& w, int split, int part, cudaStream_t st, int* launches) {
     const int L = w.nlev;
+    if (split > L - 1) split = L - 1;
     int n = 0;
-    for (int l = 0; l + 1 < L; ++l) {
-        Level &v = w.lev[l], &c = w.lev[l + 1];
-        down_kernel<<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.b, v.m, v.x, c.m, c.b, v.ny, v.nx, c.ny, c.nx,
-                                                               w.has_above, w.has_below);
-        ++n;
-    }
-    {   // coarsest level: a fixed number of sweeps (a symmetric operator, like the rest of the cycle)
-        Level& v = w.lev[L - 1];
-        const int g = tile_grid(v.ny, v.nx);
-        smooth_kernel<true><<<g, kBlock, 0, st>>>(nullptr, v.x, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
-        float *a = v.x, *b = v.y;
-        for (int s2 = 1; s2 < kCoarsestSweeps; ++s2) {
-            smooth_kernel<false><<<g, kBlock, 0, st>>>(a, b, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
-            float* t = a; a = b; b = t;
+    if (part == 0) {
+        for (int l = 0; l < split; ++l) {
+            Level &v = w.lev[l], &c = w.lev[l + 1];
+            down_kernel<<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.b, v.m, v.x, c.m, c.b, v.ny, v.nx, c.ny, c.nx,
+                                                                   w.has_above, w.has_below);
+            ++n;
         }
-        n += kCoarsestSweeps;
-        // kCoarsestSweeps is even: the result sits in v.y, as on every other level
-    }
-    for (int l = L - 2; l >= 0; --l) {
-        Level &v = w.lev[l], &c = w.lev[l + 1];
-        up_kernel<<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.x, c.y, v.b, v.m, v.y, v.ny, v.nx, c.nx, w.has_above,
-                                                             w.has_below);
-        ++n;
+    } else if (part == 1) {
+        for (int l = split; l + 1 < L; ++l) {
+            Level &v = w.lev[l], &c = w.lev[l + 1];
+            down_kernel<<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.b, v.m, v.x, c.m, c.b, v.ny, v.nx, c.ny, c.nx,
+                                                                   w.has_above, w.has_below);
+            ++n;
+        }
+        {   // coarsest level: a fixed number of sweeps (a symmetric operator, like the rest of the cycle)
+            Level& v = w.lev[L - 1];
+            const int g = tile_grid(v.ny, v.nx);
+            smooth_kernel<true><<<g, kBlock, 0, st>>>(nullptr, v.x, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
+            float *a = v.x, *b = v.y;
+            for (int s2 = 1; s2 < kCoarsestSweeps; ++s2) {
+                smooth_kernel<false><<<g, kBlock, 0, st>>>(a, b, v.b, v.m, v.ny, v.nx, w.has_above, w.has_below);
+                float* t = a; a = b; b = t;
+            }
+            n += kCoarsestSweeps;
+            // kCoarsestSweeps is even: the result sits in v.y, as on every other level
+        }
+        for (int l = L - 2; l >= split; --l) {
+            Level &v = w.lev[l], &c = w.lev[l + 1];
+            up_kernel<<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.x, c.y, v.b, v.m, v.y, v.ny, v.nx, c.nx,
+                                                                 w.has_above, w.has_below);
+            ++n;
+        }
+    } else {
+        for (int l = split - 1; l >= 0; --l) {
+            Level &v = w.lev[l], &c = w.lev[l + 1];
+            up_kernel<<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.x, c.y, v.b, v.m, v.y, v.ny, v.nx, c.nx,
+                                                                 w.has_above, w.has_below);
+            ++n;
+        }
     }
     *launches += n;
+}
+
+// z = M^-1 b0: one whole cycle; the level-0 result is left in lev[0].y
+static const float* vcycle(Ws& w, cudaStream_t st, int* launches) {
+    vcycle_part(w, 0, 1, st, launches);
     return w.lev[0].y;
 }
 
@@ -823,8 +849,8 @@ int smrf_inpaint_start(const void* grid, int64_t ny, int64_t nx, int dtype, void
 }
 
 int smrf_inpaint_step(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, int has_above, int has_below,
-                      int k, int phase, const double* p_above, const double* p_below, const uint8_t* m_above,
-                      const uint8_t* m_below, void* stream) {
+                      int k, int phase, const float* z_ext, const double* p_above, const double* p_below,
+                      const uint8_t* m_above, const uint8_t* m_below, void* stream) {
     SMRF_CHECK_ARG(k >= 0 && k < kMaxIter, "iteration index out of range");
     Ws w;
     if (int rc = check_ws("smrf_inpaint_step", workspace, workspace_bytes, ny, nx, has_above, has_below, &w)) return rc;
@@ -832,7 +858,7 @@ int smrf_inpaint_step(int64_t ny, int64_t nx, void* workspace, size_t workspace_
     const int g2 = tile_grid(ny, nx);
     const bool jacobi = use_jacobi();
     int launches = 0;
-    const float* z = w.lev[0].y;   // where vcycle() leaves its result
+    const float* z = z_ext ? z_ext : w.lev[0].y;   // where vcycle() leaves its result, unless the caller preconditions
     switch (phase) {
         case 0:   // z = M^-1 r (local V-cycle), rz[k] += r.z over this band
             if (jacobi) rz_kernel<true><<<g2, kBlock, 0, st>>>(w, nullptr, ny, nx, k);
@@ -840,6 +866,11 @@ int smrf_inpaint_step(int64_t ny, int64_t nx, void* workspace, size_t workspace_
                 z = vcycle(w, st, &launches);
                 rz_kernel<false><<<g2, kBlock, 0, st>>>(w, z, ny, nx, k);
             }
+            ++launches;
+            break;
+        case 20:  // the caller has preconditioned (z_ext = M^-1 r on this band): rz[k] += r.z only
+            SMRF_CHECK_ARG(z_ext, "phase 20 needs z_ext");
+            rz_kernel<false><<<g2, kBlock, 0, st>>>(w, z, ny, nx, k);
             ++launches;
             break;
         case 1:   // p = z + (rz[k]/rz[k-1]) p      (rz[k] must be complete: all-reduced)
@@ -859,6 +890,58 @@ int smrf_inpaint_step(int64_t ny, int64_t nx, void* workspace, size_t workspace_
         default:
             SMRF_CHECK_ARG(false, "bad phase");
     }
+    SMRF_LAUNCH_CHECK();
+    count_launches(launches);
+    return 0;
+}
+
+// ---- a multigrid hierarchy on its own (the replicated global coarse grid of the band solver) ----
+int smrf_mg_level_layout(int64_t ny, int64_t nx, int level, int64_t* out6_host) {
+    SMRF_CHECK_ARG(out6_host && ny > 0 && nx > 0 && level >= 0, "bad argument");
+    Ws w;
+    carve(nullptr, ny, nx, &w);
+    SMRF_CHECK_ARG(level < w.nlev, "no such level");
+    const Level& v = w.lev[level];
+    out6_host[0] = v.ny; out6_host[1] = v.nx;
+    out6_host[2] = (int64_t)(uintptr_t)v.m; out6_host[3] = (int64_t)(uintptr_t)v.x;
+    out6_host[4] = (int64_t)(uintptr_t)v.y; out6_host[5] = (int64_t)(uintptr_t)v.b;
+    return 0;
+}
+
+int smrf_mg_setup_mask(const uint8_t* mask, int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, void* stream) {
+    SMRF_CHECK_ARG(mask, "null mask");
+    Ws w;
+    if (int rc = check_ws("smrf_mg_setup_mask", workspace, workspace_bytes, ny, nx, 0, 0, &w)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    SMRF_CUDA(cudaMemcpyAsync(w.lev[0].m, mask, (size_t)ny * nx, cudaMemcpyDeviceToDevice, st));
+    int launches = 0;
+    for (int l = 0; l + 1 < w.nlev; ++l) {
+        Level &f = w.lev[l], &c = w.lev[l + 1];
+        coarsen_kernel<<<tile_grid(c.ny, c.nx), kBlock, 0, st>>>(f.m, c.m, f.ny, f.nx, c.ny, c.nx);
+        ++launches;
+    }
+    SMRF_LAUNCH_CHECK();
+    count_launches(launches);
+    return 0;
+}
+
+int smrf_mg_cycle_part(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, int has_above, int has_below,
+                       int split, int part, void* stream) {
+    SMRF_CHECK_ARG(split >= 0 && part >= 0 && part <= 2, "bad split / part");
+    Ws w;
+    if (int rc = check_ws("smrf_mg_cycle_part", workspace, workspace_bytes, ny, nx, has_above, has_below, &w)) return rc;
+    int launches = 0;
+    vcycle_part(w, split, part, (cudaStream_t)stream, &launches);
+    SMRF_LAUNCH_CHECK();
+    count_launches(launches);
+    return 0;
+}
+
+int smrf_mg_vcycle(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, void* stream) {
+    Ws w;
+    if (int rc = check_ws("smrf_mg_vcycle", workspace, workspace_bytes, ny, nx, 0, 0, &w)) return rc;
+    int launches = 0;
+    vcycle(w, (cudaStream_t)stream, &launches);
     SMRF_LAUNCH_CHECK();
     count_launches(launches);
     return 0;
@@ -915,7 +998,7 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
             if (it + burst > max_iter) burst = max_iter - it;
             for (int j = 0; j < burst; ++j, ++it)
                 for (int ph = 0; ph < 4; ++ph)
-                    if (int rc = smrf_inpaint_step(ny, nx, workspace, workspace_bytes, 0, 0, it, ph, nullptr, nullptr, nullptr, nullptr, stream)) return rc;
+                    if (int rc = smrf_inpaint_step(ny, nx, workspace, workspace_bytes, 0, 0, it, ph, nullptr, nullptr, nullptr, nullptr, nullptr, stream)) return rc;
             SMRF_CUDA(cudaMemcpyAsync(&bits, &w.sc->rmax[it], 8, cudaMemcpyDeviceToHost, st));
             SMRF_CUDA(cudaStreamSynchronize(st));
             memcpy(&rmax, &bits, 8);

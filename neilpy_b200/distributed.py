@@ -34,8 +34,18 @@ SPLINE_HALO = 80
 
 
 # ------------------------------------------------------------------ partition + halo helpers
+MG_SPLIT = 3          # multigrid levels 0..2 run on the (ghost-extended) band, level 3 and coarser on the global grid
+MG_GHOST = 48         # ghost rows per side for those levels: a multiple of 2**MG_SPLIT, >= their dependency radius (~37)
+
+
 def rows_per_band(ny, world):
-    return (ny + world - 1) // world
+    """Equal bands; with several ranks a multiple of 2**MG_SPLIT rows so that the cells of the
+    first global multigrid level never straddle two bands."""
+    per = (ny + world - 1) // world
+    if world > 1:
+        q = 1 << MG_SPLIT
+        per = (per + q - 1) // q * q
+    return per
 
 
 def band_bounds(ny, world, rank):
@@ -49,7 +59,7 @@ def check_partition(ny, world, halo):
     """Every band must be able to serve its neighbours' halos from its own rows."""
     for r in range(world):
         r0, r1 = band_bounds(ny, world, r)
-        if r1 - r0 < halo and world > 1:
+        if (r1 - r0 < halo or r1 - r0 < 1) and world > 1:
             raise ValueError('grid of %d rows is too short for %d bands with a %d-row halo' % (ny, world, halo))
 
 
@@ -90,7 +100,7 @@ def _api():
     return _lib, api
 
 
-def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None):
+def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None, r0=None):
     """Distributed multigrid-preconditioned CG on a row band (see module docstring)."""
     _lib, api = _api()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -121,6 +131,71 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None):
         return info, ws
     mean = s_known / n_known if n_known else 0.0
     m_above, m_below = exchange_halo(m, 1, group)
+    # The preconditioner is the GLOBAL V-cycle, evaluated band by band: levels < MG_SPLIT run on the
+    # band extended by MG_GHOST ghost rows (recomputed redundantly; deeper than the cycle's
+    # dependency radius, so the owned rows come out exactly as on one GPU), levels >= MG_SPLIT run
+    # on a hierarchy of the global coarse grid that every rank holds.
+    ext = None
+    lv = (C.c_int64 * 6)()
+    if world > 1 and per is not None and r0 is not None:
+        G = MG_GHOST
+        mE, top = with_halo(m, G, group)
+        mE = mE.contiguous()
+        nyE = mE.shape[0]
+        bot = nyE - top - ny
+        if lib.smrf_mg_level_layout(nyE, nx, MG_SPLIT + 1, lv) == 0:
+            f32 = lambda w_, off, a_, b_: w_[off:off + 4 * a_ * b_].view(torch.float32).view(a_, b_)
+            wsE = torch.empty(lib.smrf_inpaint_workspace_bytes(nyE, nx), dtype=torch.uint8, device=band.device)
+            _lib.check(lib.smrf_mg_setup_mask(api._ptr(mE), nyE, nx, api._ptr(wsE), wsE.numel(), st()), 'smrf_mg_setup_mask')
+            _lib.check(lib.smrf_mg_level_layout(nyE, nx, 0, lv), 'smrf_mg_level_layout')
+            _, _, _, _, e_y0, e_b0 = [int(v) for v in lv]
+            _lib.check(lib.smrf_mg_level_layout(nyE, nx, MG_SPLIT, lv), 'smrf_mg_level_layout')
+            nyLE, nxL, e_mL, _, e_yL, e_bL = [int(v) for v in lv]
+            tL, nyL, perL = top >> MG_SPLIT, (ny + (1 << MG_SPLIT) - 1) >> MG_SPLIT, per >> MG_SPLIT
+            mine_m = torch.zeros((perL, nxL), dtype=torch.uint8, device=band.device)
+            mine_m[:nyL] = wsE[e_mL:e_mL + nyLE * nxL].view(nyLE, nxL)[tL:tL + nyL]
+            all_m = torch.empty((perL * world, nxL), dtype=torch.uint8, device=band.device)
+            dist.all_gather_into_tensor(all_m, mine_m, group=group)
+            tot = torch.tensor([nyL], dtype=torch.int64, device=band.device)
+            dist.all_reduce(tot, group=group)
+            nyG = int(tot.item())                      # rows of the global level-MG_SPLIT grid (bands stack without gaps)
+            wsC = torch.empty(lib.smrf_inpaint_workspace_bytes(nyG, nxL), dtype=torch.uint8, device=band.device)
+            _lib.check(lib.smrf_mg_setup_mask(api._ptr(all_m), nyG, nxL, api._ptr(wsC), wsC.numel(), st()), 'smrf_mg_setup_mask')
+            _lib.check(lib.smrf_mg_level_layout(nyG, nxL, 0, lv), 'smrf_mg_level_layout')
+            _, _, _, _, c_y, c_b = [int(v) for v in lv]
+            _lib.check(lib.smrf_mg_level_layout(ny, nx, 0, lv), 'smrf_mg_level_layout')
+            band_b0 = f32(ws, int(lv[5]), ny, nx)           # (float) r on the unknown cells, kept by the CG kernels
+            y0E = f32(wsE, e_y0, nyE, nx)
+            ext = dict(G=G, top=top, nyE=nyE, nyLE=nyLE, nxL=nxL, tL=tL, nyL=nyL, perL=perL, nyG=nyG, ws=wsE, wsC=wsC,
+                       haE=int(r0 - top > 0), hbE=int(bot > 0 or rank < world - 1), band_b0=band_b0,
+                       b0E=f32(wsE, e_b0, nyE, nx), z=y0E[top:top + ny],
+                       bLE=f32(wsE, e_bL, nyLE, nxL), yLE=f32(wsE, e_yL, nyLE, nxL),
+                       cb=f32(wsC, c_b, nyG, nxL), cy=f32(wsC, c_y, nyG, nxL), g0=rank * perL - tL,
+                       mine=torch.zeros((perL, nxL), dtype=torch.float32, device=band.device),
+                       full=torch.empty((perL * world, nxL), dtype=torch.float32, device=band.device))
+    z_ptr = api._ptr(ext['z']) if ext is not None else None
+
+    def precondition(k):
+        if ext is None:
+            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 0, None, None, None, None, None, st()), 'step0')
+            return
+        e = ext
+        above, below = exchange_halo(e['band_b0'], e['G'], group)
+        if above is not None:
+            e['b0E'][:e['top']] = above
+        e['b0E'][e['top']:e['top'] + ny] = e['band_b0']
+        if below is not None:
+            e['b0E'][e['top'] + ny:] = below
+        wE, nE = api._ptr(e['ws']), e['ws'].numel()
+        _lib.check(lib.smrf_mg_cycle_part(e['nyE'], nx, wE, nE, e['haE'], e['hbE'], MG_SPLIT, 0, st()), 'mg down')
+        e['mine'][:e['nyL']] = e['bLE'][e['tL']:e['tL'] + e['nyL']]
+        dist.all_gather_into_tensor(e['full'], e['mine'], group=group)
+        e['cb'].copy_(e['full'][:e['nyG']])
+        _lib.check(lib.smrf_mg_vcycle(e['nyG'], e['nxL'], api._ptr(e['wsC']), e['wsC'].numel(), st()), 'smrf_mg_vcycle')
+        e['yLE'].copy_(e['cy'][e['g0']:e['g0'] + e['nyLE']])
+        _lib.check(lib.smrf_mg_cycle_part(e['nyE'], nx, wE, nE, e['haE'], e['hbE'], MG_SPLIT, 2, st()), 'mg up')
+        _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 20, z_ptr, None, None, None, None, st()), 'step20')
+
     _lib.check(lib.smrf_inpaint_start(api._ptr(band), ny, nx, code, wp, wn, ha, hb, mean, api._ptr(guess), 0, None, None, st()), 'start0')
     u_above, u_below = exchange_halo(u, 1, group)
     _lib.check(lib.smrf_inpaint_start(api._ptr(band), ny, nx, code, wp, wn, ha, hb, mean, None, 1, api._ptr(u_above),
@@ -135,14 +210,14 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None):
     while r > tol and it < max_iter:
         for _ in range(burst):
             k = it
-            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 0, None, None, None, None, st()), 'step0')
+            precondition(k)
             dist.all_reduce(rz[k:k + 1], group=group)
-            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 1, None, None, None, None, st()), 'step1')
+            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 1, z_ptr, None, None, None, None, st()), 'step1')
             p_above, p_below = exchange_halo(p, 1, group)
-            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 2, api._ptr(p_above), api._ptr(p_below),
+            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 2, None, api._ptr(p_above), api._ptr(p_below),
                                              api._ptr(m_above), api._ptr(m_below), st()), 'step2')
             dist.all_reduce(pq[k:k + 1], group=group)
-            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 3, None, None, None, None, st()), 'step3')
+            _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 3, None, None, None, None, None, st()), 'step3')
             it += 1
         r = residual(it)
         if not (r == r):
@@ -276,7 +351,7 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     nx, ny = len(xedges) - 1, len(yedges) - 1
     mark('extent')
     wmax = int(windows.max()) if len(windows) else 1
-    check_partition(ny, world, max(2 * wmax, SPLINE_HALO))
+    check_partition(ny, world, max(2 * wmax, SPLINE_HALO, MG_GHOST))
     t = api._make_transform(xedges[0], yedges[0], cellsize)
     inv6 = api._inverse6(t)
     per = rows_per_band(ny, world)
@@ -304,7 +379,7 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     mark('binning')
 
     # ---- inpaint, low outliers, progressive filter, punch, inpaint
-    info1, ws = _inpaint_band(lib, Zmin, None, tol, group)
+    info1, ws = _inpaint_band(lib, Zmin, None, tol, group, per=per, r0=r0)
     mark('inpaint1')
     low = torch.zeros((rows, nx), dtype=torch.uint8, device=dev)
     one = np.array([1])
@@ -319,7 +394,7 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     _lib.check(lib.smrf_merge_punch(api._ptr(Zmin), api._ptr(empty), api._ptr(low), api._ptr(obj),
                                     api._ptr(object_cells), rows, nx, code, st()), 'smrf_merge_punch')
     Zpro = Zmin
-    info2, ws = _inpaint_band(lib, Zpro, ws, tol, group, guess=None if os.environ.get('SMRF_NO_GUESS') else opened)
+    info2, ws = _inpaint_band(lib, Zpro, ws, tol, group, guess=opened, per=per, r0=r0)
     del opened
     del ws
     mark('inpaint2')

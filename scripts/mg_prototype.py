@@ -1,3 +1,4 @@
+import os
 """numpy prototype of the multigrid-preconditioned CG used by the CUDA harmonic inpainter
 (design exploration; not used by the product or the tests)."""
 import sys, time
@@ -151,3 +152,78 @@ def nu_experiment():
 
 if len(sys.argv) > 1 and sys.argv[1] == 'nu':
     nu_experiment()
+
+
+def band_experiment2(split=3):
+    """block-Jacobi over two bands vs bands with global coarse levels (>= split), larger grid"""
+    x, y, z, _ = O.synth_cloud(2000000, 1000.0, 1000.0, seed=0)
+    Zmin, t = O.create_dem(x, y, z, 1, 'min')
+    # cheap stand-in for the punched surface: empty cells + the generator's building footprints
+    import scipy.ndimage as ndi
+    G = Zmin.copy()
+    emp = np.isnan(G)
+    filled = O.harmonic_fill_exact(G)
+    obj = O.progressive_filter(filled, np.arange(1, 19), 1, .15)
+    G[obj] = np.nan
+    unk = np.isnan(G)
+    print('grid', G.shape, 'unknown', unk.mean())
+    deg = deg_of(unk.shape)
+    ny = G.shape[0]; h = (ny // 2) // 8 * 8
+
+    class BandMG(MG):
+        def __init__(self, unk, above, below, **kw):
+            super().__init__(unk, **kw)
+            self.levels = [(u, d + (np.arange(d.shape[0])[:, None] == 0) * above + (np.arange(d.shape[0])[:, None] == d.shape[0] - 1) * below)
+                           for (u, d) in self.levels]
+    closure = int(os.environ.get('CLOSURE', '1'))
+    top, bot = BandMG(unk[:h], 0, closure, nu=2), BandMG(unk[h:], closure, 0, nu=2)
+    full = MG(unk, nu=2)
+
+    def two_level(r):
+        # band-local levels < split, global levels >= split
+        def down(mg, l, b, xs, bs):
+            unk_, deg_ = mg.levels[l]
+            xx = mg.smooth(l, np.zeros_like(b), b, mg.nu)
+            rr = np.where(unk_, b - applyA(xx, unk_, deg_), 0.0)
+            uc, _ = mg.levels[l + 1]
+            xs.append(xx); bs.append(b)
+            return np.where(uc, restrict(rr, uc.shape), 0.0)
+        outs = []
+        state = []
+        for mg, rb in ((top, r[:h]), (bot, r[h:])):
+            xs, bs = [], []
+            b = rb
+            for l in range(split):
+                b = down(mg, l, b, xs, bs)
+            state.append((mg, xs, bs, b))
+        bc = np.vstack([state[0][3], state[1][3]])
+        ec = full.vcycle(split, bc)                      # global coarse part
+        hc = state[0][3].shape[0]
+        for (mg, xs, bs, _), e in zip(state, (ec[:hc], ec[hc:])):
+            for l in range(split - 1, -1, -1):
+                unk_, deg_ = mg.levels[l]
+                xx = xs[l] + np.where(unk_, prolong(e, unk_.shape), 0.0)
+                e = mg.smooth(l, xx, bs[l], mg.nu)
+            outs.append(e)
+        return np.vstack(outs)
+
+    def run(M, tol=1e-7):
+        u = np.where(unk, np.nanmean(G), G)
+        s = np.zeros_like(u)
+        s[1:, :] += u[:-1, :]; s[:-1, :] += u[1:, :]; s[:, 1:] += u[:, :-1]; s[:, :-1] += u[:, 1:]
+        r = np.where(unk, s - deg * u, 0.0)
+        zz = M(r); p = zz.copy(); rz = (r * zz).sum(); it = 0
+        while np.abs(r).max() > tol and it < 500:
+            q = applyA(p, unk, deg)
+            a = rz / (p * q).sum()
+            u += a * p; r -= a * q
+            zz = M(r); rz2 = (r * zz).sum()
+            p = zz + (rz2 / rz) * p; rz = rz2; it += 1
+        return it
+    print('global V-cycle             :', run(lambda r: full.vcycle(0, r)))
+    print('two-band block V           :', run(lambda r: np.vstack([top.vcycle(0, r[:h]), bot.vcycle(0, r[h:])])))
+    print('bands + global levels >= %d :' % split, run(two_level))
+
+
+if len(sys.argv) > 1 and sys.argv[1] == 'bands2':
+    band_experiment2()
