@@ -212,8 +212,15 @@ def opening_roofline(torch, nb, Zsurf, reps, peaks):
     total_ms = float(per_w.sum())
     achieved = 18 * bytes_per_launch / (total_ms * 1e-3) / 1e9
     peak = peaks['hbm_gbs']
+    traffic = None                      # dram bytes per launch from the committed ncu capture of this grid, if any
+    tp = os.path.join(ROOT, 'profiles', 'r1_opening_traffic.json')
+    if os.path.exists(tp):
+        g = json.load(open(tp))['grids'].get('%dx%d' % (ny, nx))
+        if g:
+            traffic = g['mean_bytes_per_launch']
     roof = {'bound': 'hbm', 'kernel': 'open_march_kernel<W> (18 launches, W=1..18)', 'achieved': achieved,
-            'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peaks['source'], 'traffic': None,
+            'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peaks['source'], 'traffic': traffic,
+            'traffic_source': 'profiles/r1_opening_traffic.json (ncu dram__bytes_read+write, mean over the 18 launches)' if traffic else None,
             'algorithmic_bytes_per_launch': bytes_per_launch, 'avg_launch_ms': total_ms / 18,
             'per_window_ms': [round(float(v), 4) for v in per_w],
             'per_window_frac': [round(float(bytes_per_launch / (v * 1e-3) / 1e9 / peak), 4) for v in per_w],
