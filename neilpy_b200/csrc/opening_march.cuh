@@ -77,7 +77,7 @@ template <int W>
 struct Cfg : CfgT<W,
                   /*C=*/((W <= 10 || W == 17 || W == 18) ? 4 : 2),
                   /*PAIR=*/(W != 2 && W <= 24),
-                  /*MINB=*/(W <= 4 ? 1 : (W <= 16 || W == 19 || W == 20 ? 2 : 1)),
+                  /*MINB=*/(W <= 5 ? 1 : (W <= 16 || W == 19 || W == 20 ? 2 : 1)),
                   /*U=*/4> {};
 
 struct Params {

@@ -67,7 +67,12 @@ int main(int argc, char** argv) {
     h_out.resize(N * N);
     constexpr int W = SWEEP_W;
     using namespace march;
-#ifdef SWEEP_U2
+#if defined(SWEEP_SHIPPED)
+    run<Cfg<W>>("shipped Cfg<W>");
+    run<CfgT<W, 4, true, 1, 4>>("C4 pair   MINB1 U4");
+    run<CfgT<W, 2, true, 2, 4>>("C2 pair   MINB2 U4");
+    run<CfgT<W, 4, true, 2, 4>>("C4 pair   MINB2 U4");
+#elif defined(SWEEP_U2)
     run<CfgT<W, 4, true, 1, 4>>("C4 pair   MINB1 U4");
     run<CfgT<W, 2, true, 2, 4>>("C2 pair   MINB2 U4");
     run<CfgT<W, 4, true, 1, 2>>("C4 pair   MINB1 U2");
