@@ -189,18 +189,20 @@ def opening_roofline(torch, nb, Zsurf, reps, peaks):
     ny, nx = Zsurf.shape
     windows = np.arange(18) + 1
     thr = .15 * (windows * 1)
-    a, b, tmp = Zsurf.clone(), torch.empty_like(Zsurf), torch.empty_like(Zsurf)
+    # rows padded to 16 bytes, as smrf_progressive_open lays out its ping-pong surfaces
+    pitch = (nx + 3) // 4 * 4
+    a, b, tmp = [torch.zeros((ny, pitch), dtype=Zsurf.dtype, device=Zsurf.device) for _ in range(3)]
     mask = torch.zeros(Zsurf.shape, dtype=torch.uint8, device=Zsurf.device)
     code = _code(Zsurf.dtype)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(19)] for _ in range(reps)]
     for rep in range(reps + 1):                      # rep 0 is warm-up
         cur, nxt = a, b
-        cur.copy_(Zsurf)
+        cur[:, :nx].copy_(Zsurf)
         mask.zero_()
         for i, w in enumerate(windows):
             if rep:
                 ev[rep - 1][i].record()
-            _lib.check(lib.smrf_open_window(_ptr(cur), _ptr(nxt), _ptr(tmp), _ptr(mask), None, ny, nx, code, int(w),
+            _lib.check(lib.smrf_open_window(_ptr(cur), _ptr(nxt), _ptr(tmp), _ptr(mask), None, ny, nx, pitch, code, int(w),
                                             float(thr[i]), i, 0, 0, ny, _stream()), 'smrf_open_window')
             cur, nxt = nxt, cur
         if rep:
@@ -386,7 +388,7 @@ def opening_c3(torch, nb, dev, peaks, n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--points', type=int, default=50_000_000)

@@ -180,10 +180,13 @@ int smrf_progressive_open(const void* surface, void* workspace, size_t workspace
 /* one window, out of place: `out` = opening(in, disk(window)); mask/when_dropped as above
  * (either may be NULL); `tmp` = ny*nx elements.  Only rows [row_lo,row_hi) of out/mask are
  * written: with row-band sharding the halo rows outside are inputs only (pass 0, ny
- * otherwise).  Building block of smrf_progressive_open and of the multi-GPU driver. */
+ * otherwise).  `pitch` is the row stride of in / out / tmp in elements (>= nx; mask and
+ * when_dropped are always nx wide): rows padded to 16 bytes let the marching kernels use
+ * 16-byte copies and stores for any nx (smrf_progressive_open pads its ping-pong surfaces
+ * itself).  Building block of smrf_progressive_open and of the multi-GPU driver. */
 int smrf_open_window(const void* in, void* out, void* tmp, uint8_t* mask, uint8_t* when_dropped,
-                     int64_t ny, int64_t nx, int dtype, int window, double threshold, int window_index,
-                     int negate, int64_t row_lo, int64_t row_hi, void* stream);
+                     int64_t ny, int64_t nx, int64_t pitch, int dtype, int window, double threshold,
+                     int window_index, int negate, int64_t row_lo, int64_t row_hi, void* stream);
 /* brute-force disk opening (|disk| loads per cell); the in-library cross-check of the fast kernels */
 int smrf_open_window_bruteforce(const void* in, void* out, void* tmp, int64_t ny, int64_t nx, int dtype,
                                 int window, void* stream);

@@ -45,7 +45,7 @@ SIGNATURES = {
     'smrf_inpaint': (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _dbl, _i32, _dp, _vp]),
     'smrf_open_workspace_bytes': (_sz, [_i64, _i64, _i32, _i32]),
     'smrf_progressive_open': (_i32, [_vp, _vp, _sz, _vp, _vp, _i64, _i64, _i32, _ip, _dp, _i32, _i32, _vp, _vp]),
-    'smrf_open_window': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _dbl, _i32, _i32, _i64, _i64, _vp]),
+    'smrf_open_window': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _dbl, _i32, _i32, _i64, _i64, _vp]),
     'smrf_open_window_bruteforce': (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     'smrf_merge_punch': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
     'smrf_slope': (_i32, [_vp, _vp, _i64, _i64, _i32, _dbl, _vp]),

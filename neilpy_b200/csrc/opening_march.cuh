@@ -85,7 +85,7 @@ struct Params {
     float* out;
     uint8_t* mask;
     uint8_t* when;
-    int64_t ny, nx, row_lo, row_hi;
+    int64_t ny, nx, pitch, row_lo, row_hi;   // pitch: row stride of in/out in elements (>= nx); mask/when are nx wide
     int seg;
     double thr;
     int widx, vec_ok;
@@ -261,7 +261,7 @@ __device__ __forceinline__ void issue_group(const Params& p, float* Zs, int g, i
         if (rr >= K::U) break;
         const int64_t r = zr0 + (int64_t)g * K::U + rr;
         const bool rowok = r >= 0 && r < p.ny;
-        const float* src = p.in + r * p.nx + zc0;
+        const float* src = p.in + r * p.pitch + zc0;
         float* dst = slot + (size_t)rr * K::COLS;
         for (int cc = lane; cc < NCH; cc += 32) {
             const int64_t g0 = zc0 + (int64_t)cc * VL;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, K::MINB) open_march_kernel(const Par
 #pragma unroll
                 for (int c = 0; c < C; ++c) l[c] = 0.f;
                 if (emit) {
-                    const int64_t off = d * p.nx + gx;
+                    const int64_t off = d * p.pitch + gx;
                     if (vec) load_vec<C>(p.in + off, l);
                     else {
 #pragma unroll
@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(kThreads, K::MINB) open_march_kernel(const Par
                 return emit;
             };
             auto put = [&](int u, const float (&fin)[C], const float (&l)[C]) {
-                const int64_t off = (y0 + (int64_t)dg * U + u) * p.nx + gx;
+                const int64_t off = (y0 + (int64_t)dg * U + u) * p.pitch + gx;
+                const int64_t moff = (y0 + (int64_t)dg * U + u) * p.nx + gx;
                 if (p.out) {
                     float o[C];
 #pragma unroll
@@ -435,8 +436,8 @@ __global__ void __launch_bounds__(kThreads, K::MINB) open_march_kernel(const Par
                         const double df = NEG ? __dsub_rn((double)fin[c], (double)l[c])
                                               : __dsub_rn((double)l[c], (double)fin[c]);
                         if ((gx + c < p.nx) && (df > p.thr)) {
-                            p.mask[off + c] = 1;
-                            if (p.when) p.when[off + c] = (uint8_t)p.widx;
+                            p.mask[moff + c] = 1;
+                            if (p.when) p.when[moff + c] = (uint8_t)p.widx;
                         }
                     }
                 }
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, K::MINB) open_march_kernel(const Par
 
 template <typename K, bool NEG>
 int launch_open_march_cfg(const float* in, float* out, uint8_t* mask, uint8_t* when, int64_t ny, int64_t nx,
-                          double thr, int widx, int64_t row_lo, int64_t row_hi, cudaStream_t st) {
+                          int64_t pitch, double thr, int widx, int64_t row_lo, int64_t row_hi, cudaStream_t st) {
     constexpr int W = K::W;
     static bool attr_set = false;
     if (!attr_set) {
@@ -502,9 +503,9 @@ int launch_open_march_cfg(const float* in, float* out, uint8_t* mask, uint8_t* w
     const int nsegs = (int)((rows + seg - 1) / seg);
     march::Params p;
     p.in = in; p.out = out; p.mask = mask; p.when = when;
-    p.ny = ny; p.nx = nx; p.row_lo = row_lo; p.row_hi = row_hi;
+    p.ny = ny; p.nx = nx; p.pitch = pitch; p.row_lo = row_lo; p.row_hi = row_hi;
     p.seg = seg; p.thr = thr; p.widx = widx;
-    p.vec_ok = (nx % 4 == 0) && (((uintptr_t)in & 15) == 0) && (out == nullptr || ((uintptr_t)out & 15) == 0);
+    p.vec_ok = (pitch % 4 == 0) && (((uintptr_t)in & 15) == 0) && (out == nullptr || ((uintptr_t)out & 15) == 0);
     dim3 grid((unsigned)nstrips, (unsigned)nsegs);
     march::open_march_kernel<K, NEG><<<grid, march::kThreads, K::kSmemBytes, st>>>(p);
     SMRF_LAUNCH_CHECK();
@@ -514,8 +515,8 @@ int launch_open_march_cfg(const float* in, float* out, uint8_t* mask, uint8_t* w
 
 template <int W, bool NEG>
 int launch_open_march_f32(const float* in, float* out, uint8_t* mask, uint8_t* when, int64_t ny, int64_t nx,
-                          double thr, int widx, int64_t row_lo, int64_t row_hi, cudaStream_t st) {
-    return launch_open_march_cfg<march::Cfg<W>, NEG>(in, out, mask, when, ny, nx, thr, widx, row_lo, row_hi, st);
+                          int64_t pitch, double thr, int widx, int64_t row_lo, int64_t row_hi, cudaStream_t st) {
+    return launch_open_march_cfg<march::Cfg<W>, NEG>(in, out, mask, when, ny, nx, pitch, thr, widx, row_lo, row_hi, st);
 }
 
 }  // namespace smrf

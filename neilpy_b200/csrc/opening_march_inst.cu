@@ -10,7 +10,7 @@
 
 namespace smrf {
 #define SMRF_INST(W, NEG)                                                                                     \
-    template int launch_open_march_f32<W, NEG>(const float*, float*, uint8_t*, uint8_t*, int64_t, int64_t, double, \
+    template int launch_open_march_f32<W, NEG>(const float*, float*, uint8_t*, uint8_t*, int64_t, int64_t, int64_t, double, \
                                                int, int64_t, int64_t, cudaStream_t);
 #if SMRF_W_LO <= 1 && 1 <= SMRF_W_HI
 SMRF_INST(1, false)

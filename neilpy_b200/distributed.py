@@ -287,7 +287,7 @@ def _open_windows_band(lib, band, windows, thresholds, mask, when, negate, group
             v0 = v0 + 2 * w if top else 0
             v1 = v1 - 2 * w if bot else nb
             _lib.check(lib.smrf_open_window(api._ptr(a), api._ptr(b), api._ptr(tmp), api._ptr(mbuf), api._ptr(wbuf),
-                                            nb, nx, code, w, float(thresholds[i]), i, int(negate), v0, v1, st()),
+                                            nb, nx, nx, code, w, float(thresholds[i]), i, int(negate), v0, v1, st()),
                        'smrf_open_window')
             last = b[top:top + rows]
             if len(windows) > 1:          # neilpy.py:1675-1676: last_surface advances only then

@@ -53,7 +53,7 @@ def test_opening_properties_8192(env, w):
         out, tmp = torch.empty_like(A), torch.empty_like(A)
         mask = torch.zeros(A.shape, dtype=torch.uint8, device='cuda')
         _lib.check(lib.smrf_open_window(_ptr(A), _ptr(out), _ptr(tmp), _ptr(mask), None, A.shape[0], A.shape[1],
-                                        _code(A.dtype), w, float(thr), 0, 0, 0, A.shape[0], _stream()), 'open')
+                                        A.shape[1], _code(A.dtype), w, float(thr), 0, 0, 0, A.shape[0], _stream()), 'open')
         return out, mask
 
     O1, m1 = opening(Z, 0.15 * w)

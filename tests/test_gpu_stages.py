@@ -98,7 +98,7 @@ def open_window(nb, Z, w, thr=0.0, negate=0, rows=None):
     mask = torch.zeros(zin.shape, dtype=torch.uint8, device='cuda')
     ny, nx = zin.shape
     lo, hi = rows if rows else (0, ny)
-    _lib.check(lib.smrf_open_window(_ptr(zin), _ptr(out), _ptr(tmp), _ptr(mask), None, ny, nx, _code(zin.dtype), w,
+    _lib.check(lib.smrf_open_window(_ptr(zin), _ptr(out), _ptr(tmp), _ptr(mask), None, ny, nx, nx, _code(zin.dtype), w,
                                     float(thr), 0, negate, lo, hi, _stream()), 'smrf_open_window')
     torch.cuda.synchronize()
     return out.cpu().numpy(), mask.cpu().numpy().astype(bool)
@@ -155,6 +155,28 @@ def test_open_window_row_band(nb):
     b0, b1 = lo - 2 * w, hi + 2 * w
     band, bm = open_window(nb, Z[b0:b1], w, thr=0.5, rows=(2 * w, 2 * w + hi - lo))
     assert np.array_equal(band[2 * w:2 * w + hi - lo], full[lo:hi]) and np.array_equal(bm[2 * w:2 * w + hi - lo], fm[lo:hi])
+
+
+@pytest.mark.parametrize('w', [1, 2, 7, 13, 18, 30, 45])
+def test_open_window_with_padded_rows(nb, w):
+    """row stride > nx (what smrf_progressive_open uses internally): same result as contiguous rows"""
+    import torch
+    from neilpy_b200 import _lib
+    from neilpy_b200.api import _ptr, _stream, _code
+    lib = _lib.load()
+    Z = surface(150, 1001, w + 50, np.float32)                  # nx = 1001: not a multiple of 4
+    ref, rmask = open_window(nb, Z, w, thr=0.1 * w)
+    ny, nx, pitch = 150, 1001, 1004
+    zin = torch.full((ny, pitch), 1e30, dtype=torch.float32, device='cuda')    # poison in the padding
+    zin[:, :nx] = torch.as_tensor(Z).cuda()
+    out = torch.full((ny, pitch), -7.0, dtype=torch.float32, device='cuda')
+    tmp = torch.empty_like(out)
+    mask = torch.zeros((ny, nx), dtype=torch.uint8, device='cuda')
+    _lib.check(lib.smrf_open_window(_ptr(zin), _ptr(out), _ptr(tmp), _ptr(mask), None, ny, nx, pitch, _code(zin.dtype),
+                                    w, 0.1 * w, 0, 0, 0, ny, _stream()), 'smrf_open_window')
+    torch.cuda.synchronize()
+    assert np.array_equal(out[:, :nx].cpu().numpy(), ref) and np.array_equal(mask.cpu().numpy().astype(bool), rmask)
+    assert bool((out[:, nx:] == -7.0).all())                    # the padding is never written
 
 
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])

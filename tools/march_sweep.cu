@@ -30,12 +30,12 @@ void run(const char* name) {
     cudaMemset(d_mask, 0, N * N);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    int rc = launch_open_march_cfg<K, false>(d_in, d_out, d_mask, nullptr, N, N, 0.15 * K::W, 0, 0, N, 0);
+    int rc = launch_open_march_cfg<K, false>(d_in, d_out, d_mask, nullptr, N, N, N, 0.15 * K::W, 0, 0, N, 0);
     if (rc) { printf("W=%d %s launch failed %d\n", K::W, name, rc); return; }
     cudaDeviceSynchronize();
     const int reps = 5;
     cudaEventRecord(e0);
-    for (int i = 0; i < reps; ++i) launch_open_march_cfg<K, false>(d_in, d_out, d_mask, nullptr, N, N, 0.15 * K::W, 0, 0, N, 0);
+    for (int i = 0; i < reps; ++i) launch_open_march_cfg<K, false>(d_in, d_out, d_mask, nullptr, N, N, N, 0.15 * K::W, 0, 0, N, 0);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
