@@ -209,16 +209,20 @@ int smrf_slope(const void* grid, void* slope, int64_t ny, int64_t nx, int dtype,
  * (neilpy_b200.spline.notaknot_factors) and passes, per axis, a DEVICE array of 5*n
  * doubles {l1, l2, 1/pivot, u1, u2} (banded LU without pivoting; row_factors for the
  * ny-long axis, col_factors for the nx-long one).  Intermediates are float64 in
- * `workspace`.  `coef` may alias `grid`.  ny, nx >= 4 (FITPACK raises otherwise). */
+ * `workspace`.  Coefficient (i, j) is written to coef[(i*nx + j)*coef_stride + coef_offset]:
+ * stride 1 / offset 0 is a plain grid (and may alias `grid`); stride 2 with offsets 0 and 1
+ * interleaves the DTM's and the slope raster's coefficients so that smrf_classify fetches both
+ * splines' taps from the same sectors.  ny, nx >= 4 (FITPACK raises otherwise). */
 size_t smrf_spline_workspace_bytes(int64_t ny, int64_t nx);
-int smrf_spline_prefilter(const void* grid, void* coef, int64_t ny, int64_t nx, int dtype,
-                          const double* row_factors, const double* col_factors, void* workspace,
-                          size_t workspace_bytes, void* stream);
+int smrf_spline_prefilter(const void* grid, void* coef, int64_t coef_stride, int64_t coef_offset,
+                          int64_t ny, int64_t nx, int dtype, const double* row_factors,
+                          const double* col_factors, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- interpolate + classify ----------------------------------- neilpy.py:1772-1795
  * For every point: (c, r) = ~t*(x, y); elevation = spline(Zpro).ev(r, c);
  * slope = spline(S).ev(r, c) (arguments clamped to the centre range as FITPACK's bispeu
  * does); is_object = |elevation - z| > elevation_threshold + elevation_scaler*slope.
+ * coef_s == NULL: coef_z holds interleaved (DTM, slope) coefficient pairs, [ny][nx][2].
  * Optional outputs (may be NULL): elevation, slope_out (float64 per point),
  * when_dropped_pt = drop_raster[round(r), round(c)] if drop_raster != NULL. */
 int smrf_classify(const void* x, const void* y, const void* z, int64_t n, int point_fmt,

@@ -50,7 +50,7 @@ SIGNATURES = {
     'smrf_merge_punch': (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
     'smrf_slope': (_i32, [_vp, _vp, _i64, _i64, _i32, _dbl, _vp]),
     'smrf_spline_workspace_bytes': (_sz, [_i64, _i64]),
-    'smrf_spline_prefilter': (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    'smrf_spline_prefilter': (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     'smrf_classify': (_i32, [_vp, _vp, _vp, _i64, _i32, _dp, _vp, _vp, _i64, _i64, _i32, _dbl, _dbl,
                              _vp, _vp, _vp, _vp, _vp, _vp]),
 }

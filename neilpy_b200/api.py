@@ -385,12 +385,13 @@ def smrf(x, y=None, z=None, cellsize=1, windows=5, slope_threshold=.15, elevatio
     S = torch.empty_like(Zpro)
     _lib.check(lib.smrf_slope(_ptr(Zpro), _ptr(S), ny, nx, code, float(cellsize), st), 'smrf_slope')
     rowf, colf = _factors(ny, dev), _factors(nx, dev)
-    coef_z = torch.empty_like(Zpro)
-    _lib.check(lib.smrf_spline_prefilter(_ptr(Zpro), _ptr(coef_z), ny, nx, code, _ptr(rowf), _ptr(colf), _ptr(ws),
+    # the two coefficient sets are interleaved, [ny][nx][2]: one gather sector serves both splines
+    coef = torch.empty((ny, nx, 2), dtype=Zpro.dtype, device=dev)
+    _lib.check(lib.smrf_spline_prefilter(_ptr(Zpro), _ptr(coef), 2, 0, ny, nx, code, _ptr(rowf), _ptr(colf), _ptr(ws),
                                          ws.numel(), st), 'smrf_spline_prefilter')
     if stages is not None:
         stages['S'] = S.clone()
-    _lib.check(lib.smrf_spline_prefilter(_ptr(S), _ptr(S), ny, nx, code, _ptr(rowf), _ptr(colf), _ptr(ws),
+    _lib.check(lib.smrf_spline_prefilter(_ptr(S), _ptr(coef), 2, 1, ny, nx, code, _ptr(rowf), _ptr(colf), _ptr(ws),
                                          ws.numel(), st), 'smrf_spline_prefilter')
     # --- interpolate + classify every point (:1772-1795)
     is_obj = torch.empty(pts.n, dtype=torch.uint8, device=dev)
@@ -398,11 +399,11 @@ def smrf(x, y=None, z=None, cellsize=1, windows=5, slope_threshold=.15, elevatio
     elev = torch.empty(pts.n, dtype=torch.float64, device=dev) if want_vals else None
     slp = torch.empty(pts.n, dtype=torch.float64, device=dev) if stages is not None else None
     when_pt = torch.empty(pts.n, dtype=torch.uint8, device=dev) if return_extras else None
-    _lib.check(lib.smrf_classify(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, _ptr(coef_z), _ptr(S),
+    _lib.check(lib.smrf_classify(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, _ptr(coef), None,
                                  ny, nx, code, float(elevation_threshold), float(elevation_scaler), _ptr(is_obj),
                                  _ptr(elev), _ptr(slp), _ptr(drop), _ptr(when_pt), st), 'smrf_classify')
     if stages is not None:
-        stages.update(Zpro=Zpro, object_cells=object_cells, coef_z=coef_z, coef_s=S, elevation_values=elev,
+        stages.update(Zpro=Zpro, object_cells=object_cells, coef_z=coef[:, :, 0], coef_s=coef[:, :, 1], elevation_values=elev,
                       slope_values=slp, is_object_point=is_obj, inpaint1=info1, inpaint2=info2)
 
     object_cells = object_cells.view(torch.bool)

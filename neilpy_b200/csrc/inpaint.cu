@@ -173,24 +173,40 @@ __global__ void __launch_bounds__(kBlock) scan_kernel(const T* __restrict__ grid
     }
 }
 
-// ---- u = known value, or the mean of the known cells as the starting guess ---------------
+// ---- starting guess: u = known value; an unknown cell takes the caller's guess if there is one,
+// else the mean of its known 4-neighbours (exact for an isolated empty cell, which is what more
+// than half of the empty cells of a minimum surface are), else the mean of all known cells.
 template <typename T>
 __global__ void __launch_bounds__(kBlock) init_u_kernel(const T* __restrict__ grid, const uint8_t* __restrict__ unk,
-                                                        double* __restrict__ u, int64_t n, const Scalars* sc,
-                                                        const T* __restrict__ guess) {
+                                                        double* __restrict__ u, int64_t ny, int64_t nx,
+                                                        const Scalars* sc, const T* __restrict__ guess) {
     const double mean = sc->n_known ? sc->sum_known / (double)sc->n_known : 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
-        double v;
-        if (unk[i]) {
-            v = mean;
-            if (guess) {
-                const double g = (double)guess[i];
-                if (g == g && fabs(g) < 1e300) v = g;   // a NaN / inf guess falls back to the mean
+    const Tiles T2(ny, nx);
+    SMRF_FOR_TILES(T2, y, x, in) {
+        if (in) {
+            const int64_t i = y * nx + x;
+            double v;
+            if (unk[i]) {
+                v = mean;
+                bool have = false;
+                if (guess) {
+                    const double g = (double)guess[i];
+                    if (g == g && fabs(g) < 1e300) { v = g; have = true; }   // a NaN / inf guess is ignored
+                }
+                if (!have) {
+                    double s = 0.0;
+                    int c = 0;
+                    if (y > 0 && !unk[i - nx]) { s += (double)grid[i - nx]; ++c; }
+                    if (y + 1 < ny && !unk[i + nx]) { s += (double)grid[i + nx]; ++c; }
+                    if (x > 0 && !unk[i - 1]) { s += (double)grid[i - 1]; ++c; }
+                    if (x + 1 < nx && !unk[i + 1]) { s += (double)grid[i + 1]; ++c; }
+                    if (c) v = s / (double)c;
+                }
+            } else {
+                v = (double)grid[i];
             }
-        } else {
-            v = (double)grid[i];
+            u[i] = v;
         }
-        u[i] = v;
     }
 }
 
@@ -837,8 +853,8 @@ int smrf_inpaint_start(const void* grid, int64_t ny, int64_t nx, int dtype, void
         unsigned long long one = 1;
         SMRF_CUDA(cudaMemcpyAsync(&w.sc->sum_known, &g, 8, cudaMemcpyHostToDevice, st));
         SMRF_CUDA(cudaMemcpyAsync(&w.sc->n_known, &one, 8, cudaMemcpyHostToDevice, st));
-        if (dtype == SMRF_F32) init_u_kernel<float><<<g1_for(n), kBlock, 0, st>>>((const float*)grid, w.lev[0].m, w.u, n, w.sc, (const float*)guess_grid);
-        else init_u_kernel<double><<<g1_for(n), kBlock, 0, st>>>((const double*)grid, w.lev[0].m, w.u, n, w.sc, (const double*)guess_grid);
+        if (dtype == SMRF_F32) init_u_kernel<float><<<tile_grid(ny, nx), kBlock, 0, st>>>((const float*)grid, w.lev[0].m, w.u, ny, nx, w.sc, (const float*)guess_grid);
+        else init_u_kernel<double><<<tile_grid(ny, nx), kBlock, 0, st>>>((const double*)grid, w.lev[0].m, w.u, ny, nx, w.sc, (const double*)guess_grid);
     } else {
         SMRF_CHECK_ARG((!has_above || u_above) && (!has_below || u_below), "missing halo row of u");
         residual0_kernel<<<tile_grid(ny, nx), kBlock, 0, st>>>(w, ny, nx, u_above, u_below);

@@ -112,10 +112,14 @@ static int prefilter_t(const T* grid, T* coef, double* s1, double* s2, int64_t n
     return 0;
 }
 
+// float64 intermediates -> the coefficient array, optionally interleaved with another spline's
+// coefficients (out[i * stride + offset]): the gather kernel then fetches both splines' taps from
+// the same sectors
 template <typename T>
-__global__ void __launch_bounds__(256) narrow_kernel(const double* __restrict__ in, T* __restrict__ out, int64_t n) {
+__global__ void __launch_bounds__(256) narrow_kernel(const double* __restrict__ in, T* __restrict__ out, int64_t n,
+                                                     int64_t stride, int64_t offset) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = (T)in[i];
+        out[i * stride + offset] = (T)in[i];
 }
 
 // ---- evaluation ---------------------------------------------------------------------------
@@ -167,16 +171,19 @@ __global__ void __launch_bounds__(256) classify_kernel(PointLoader<FMT> pts, int
         double hr[4], hc[4];
         const int lr = bspline4(r, ny, hr);
         const int lc = bspline4(c, nx, hc);
-        const T* pz = cz + (int64_t)(lr - 3) * nx + (lc - 3);
-        const T* ps = cs + (int64_t)(lr - 3) * nx + (lc - 3);
+        // cs == nullptr: cz holds (z, slope) coefficient pairs, [ny][nx][2]
+        const int64_t st = cs ? 1 : 2;
+        const T* pz = cz + ((int64_t)(lr - 3) * nx + (lc - 3)) * st;
+        const T* ps = cs ? cs + (int64_t)(lr - 3) * nx + (lc - 3) : pz + 1;
         double ez = 0.0, sl = 0.0;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 // FITPACK fpbisp: sp = sp + c*h(i1)*w(j1), left to right
-                ez = __dadd_rn(ez, __dmul_rn(__dmul_rn((double)__ldg(pz + a * (int64_t)nx + b), hr[a]), hc[b]));
-                sl = __dadd_rn(sl, __dmul_rn(__dmul_rn((double)__ldg(ps + a * (int64_t)nx + b), hr[a]), hc[b]));
+                const int64_t o = (a * (int64_t)nx + b) * st;
+                ez = __dadd_rn(ez, __dmul_rn(__dmul_rn((double)__ldg(pz + o), hr[a]), hc[b]));
+                sl = __dadd_rn(sl, __dmul_rn(__dmul_rn((double)__ldg(ps + o), hr[a]), hc[b]));
             }
         }
         const double required = __dadd_rn(et, __dmul_rn(es, sl));
@@ -221,11 +228,14 @@ size_t smrf_spline_workspace_bytes(int64_t ny, int64_t nx) {
     return 2 * plane;
 }
 
-int smrf_spline_prefilter(const void* grid, void* coef, int64_t ny, int64_t nx, int dtype, const double* row_factors,
-                          const double* col_factors, void* workspace, size_t workspace_bytes, void* stream) {
+int smrf_spline_prefilter(const void* grid, void* coef, int64_t coef_stride, int64_t coef_offset, int64_t ny,
+                          int64_t nx, int dtype, const double* row_factors, const double* col_factors,
+                          void* workspace, size_t workspace_bytes, void* stream) {
     SMRF_CHECK_ARG(grid && coef && row_factors && col_factors && workspace, "null pointer");
     SMRF_CHECK_ARG(ny >= 4 && nx >= 4, "the interpolating cubic spline needs at least 4 grid rows and columns");
     SMRF_CHECK_ARG(dtype == SMRF_F32 || dtype == SMRF_F64, "bad dtype");
+    SMRF_CHECK_ARG(coef_stride >= 1 && coef_offset >= 0 && coef_offset < coef_stride, "bad coefficient stride / offset");
+    SMRF_CHECK_ARG(coef_stride == 1 || coef != grid, "an interleaved coefficient array cannot alias the grid");
     if (workspace_bytes < smrf_spline_workspace_bytes(ny, nx)) {
         set_error("smrf_spline_prefilter: workspace %zu < %zu bytes", workspace_bytes, smrf_spline_workspace_bytes(ny, nx));
         return SMRF_E_WORKSPACE;
@@ -240,13 +250,13 @@ int smrf_spline_prefilter(const void* grid, void* coef, int64_t ny, int64_t nx, 
     if (g > cap) g = cap;
     if (dtype == SMRF_F32) {
         prefilter_t<float>((const float*)grid, (float*)coef, s1, s2, ny, nx, row_factors, col_factors, st);
-        narrow_kernel<float><<<g, 256, 0, st>>>(s2, (float*)coef, n);
+        narrow_kernel<float><<<g, 256, 0, st>>>(s2, (float*)coef, n, coef_stride, coef_offset);
     } else {
         prefilter_t<double>((const double*)grid, (double*)coef, s1, s2, ny, nx, row_factors, col_factors, st);
-        SMRF_CUDA(cudaMemcpyAsync(coef, s2, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+        narrow_kernel<double><<<g, 256, 0, st>>>(s2, (double*)coef, n, coef_stride, coef_offset);
     }
     SMRF_LAUNCH_CHECK();
-    count_launches(dtype == SMRF_F32 ? 7 : 6);
+    count_launches(7);
     return 0;
 }
 
@@ -254,7 +264,7 @@ int smrf_classify(const void* x, const void* y, const void* z, int64_t n, int po
                   const void* coef_z, const void* coef_s, int64_t ny, int64_t nx, int dtype,
                   double elevation_threshold, double elevation_scaler, uint8_t* is_object, double* elevation,
                   double* slope_out, const uint8_t* drop_raster, uint8_t* when_dropped_pt, void* stream) {
-    SMRF_CHECK_ARG(x && inv6_host && coef_z && coef_s && is_object, "null pointer");
+    SMRF_CHECK_ARG(x && inv6_host && coef_z && is_object, "null pointer");
     SMRF_CHECK_ARG(point_fmt == SMRF_PTS_XYZW_F32 || (y && z), "y/z null");
     SMRF_CHECK_ARG(ny >= 4 && nx >= 4 && ny < (1LL << 30) && nx < (1LL << 30), "bad grid size");
     SMRF_CHECK_ARG(dtype == SMRF_F32 || dtype == SMRF_F64, "bad dtype");

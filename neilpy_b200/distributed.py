@@ -407,29 +407,28 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     colf = api._factors(nx, dev)
     rowf_all = api._factors(ny, dev).view(5, ny)
 
-    def coefficients(band):
+    # interleaved (DTM, slope) coefficient pairs of this band, then one all-gather
+    mine = torch.zeros((per, nx, 2), dtype=tdtype, device=dev)
+    for k, band in enumerate((Zpro, S)):
         b, tp = with_halo(band, SPLINE_HALO, group)
         g0 = r0 - tp
         rf = rowf_all[:, g0:g0 + b.shape[0]].contiguous()
         wsp = torch.empty(lib.smrf_spline_workspace_bytes(b.shape[0], nx), dtype=torch.uint8, device=dev)
         c = torch.empty_like(b)
-        _lib.check(lib.smrf_spline_prefilter(api._ptr(b), api._ptr(c), b.shape[0], nx, code, api._ptr(rf),
+        _lib.check(lib.smrf_spline_prefilter(api._ptr(b), api._ptr(c), 1, 0, b.shape[0], nx, code, api._ptr(rf),
                                              api._ptr(colf), api._ptr(wsp), wsp.numel(), st()), 'smrf_spline_prefilter')
-        full = torch.zeros((per * world, nx), dtype=tdtype, device=dev)
-        mine = torch.zeros((per, nx), dtype=tdtype, device=dev)
-        mine[:rows] = c[tp:tp + rows]
-        if world > 1:
-            dist.all_gather_into_tensor(full, mine, group=group)
-        else:
-            full.copy_(mine)
-        return full[:ny]
-
-    coef_z = coefficients(Zpro)
-    coef_s = coefficients(S)
+        mine[:rows, :, k] = c[tp:tp + rows]
+        del wsp, c, b
+    full = torch.empty((per * world, nx, 2), dtype=tdtype, device=dev)
+    if world > 1:
+        dist.all_gather_into_tensor(full, mine, group=group)
+    else:
+        full.copy_(mine)
+    coef = full[:ny]
     mark('slope+spline')
     is_obj = torch.empty(pts.n, dtype=torch.uint8, device=dev)
-    _lib.check(lib.smrf_classify(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, api._ptr(coef_z),
-                                 api._ptr(coef_s), ny, nx, code, float(elevation_threshold), float(elevation_scaler),
+    _lib.check(lib.smrf_classify(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, api._ptr(coef),
+                                 None, ny, nx, code, float(elevation_threshold), float(elevation_scaler),
                                  api._ptr(is_obj), None, None, None, None, st()), 'smrf_classify')
     mark('classify')
     res = {'t': t, 'shape': (ny, nx), 'rows': (r0, r1), 'is_object_point': is_obj.view(torch.bool),

@@ -274,8 +274,8 @@ def run_tail(nb, Zpro, x, y, z, t6, cs, dtype, et=.5, es=1.25):
     ws = torch.empty(lib.smrf_spline_workspace_bytes(ny, nx), dtype=torch.uint8, device=dev)
     cz = torch.empty_like(Zt)
     rf, cf = _factors(ny, dev), _factors(nx, dev)
-    _lib.check(lib.smrf_spline_prefilter(_ptr(Zt), _ptr(cz), ny, nx, code, _ptr(rf), _ptr(cf), _ptr(ws), ws.numel(), _stream()), 'pre')
-    _lib.check(lib.smrf_spline_prefilter(_ptr(S), _ptr(S), ny, nx, code, _ptr(rf), _ptr(cf), _ptr(ws), ws.numel(), _stream()), 'pre')
+    _lib.check(lib.smrf_spline_prefilter(_ptr(Zt), _ptr(cz), 1, 0, ny, nx, code, _ptr(rf), _ptr(cf), _ptr(ws), ws.numel(), _stream()), 'pre')
+    _lib.check(lib.smrf_spline_prefilter(_ptr(S), _ptr(S), 1, 0, ny, nx, code, _ptr(rf), _ptr(cf), _ptr(ws), ws.numel(), _stream()), 'pre')
     xt, yt, zt = [torch.as_tensor(v).cuda() for v in (x, y, z)]
     n = xt.numel()
     obj = torch.empty(n, dtype=torch.uint8, device=dev)
