@@ -3,7 +3,7 @@ import os
 (design exploration; not used by the product or the tests)."""
 import sys, time
 import numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..'))
 from oracle import smrf_oracle as O
 
 def deg_of(shape):
