@@ -196,8 +196,10 @@ def _to_host(t):
             _pinned.clear()
         buf = _pinned[key] = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
     buf.copy_(t.reshape(-1), non_blocking=True)
+    out = torch.empty(tuple(t.shape), dtype=t.dtype)          # pageable; filled by torch's threaded host copy
     torch.cuda.current_stream().synchronize()
-    return buf.numpy().reshape(tuple(t.shape)).copy()
+    out.copy_(buf.view(tuple(t.shape)))
+    return out.numpy()
 
 
 def _workspace(nbytes, dev):
