@@ -394,7 +394,7 @@ def main():
     ap.add_argument('--points', type=int, default=50_000_000)
     ap.add_argument('--cpu-points', type=int, default=600_000, help='sample size of the cpu_baseline leg (0 = skip)')
     ap.add_argument('--ref-points', type=int, default=300_000, help='points per worker cloud of --impl reference')
-    ap.add_argument('--c3', type=int, default=16384, help='side of the opening-only grid (0 = skip; 32768 = config 3)')
+    ap.add_argument('--c3', type=int, default=32768, help='side of the opening-only grid (BASELINE.json configs[2]; 0 = skip)')
     args = ap.parse_args()
     args.warmup_ref = min(args.warmup, 1)
     if args.impl == 'reference':
