@@ -8,7 +8,7 @@
 // HBM, preconditioned by one geometric multigrid V(2,2)-cycle per iteration:
 //   - cell-centred 2x2 coarsening; a coarse cell is unknown only if all its children are
 //     (the coarse domains shrink, so Dirichlet data never leaks into a correction);
-//   - damped-Jacobi smoothing, piecewise-constant prolongation and its transpose as the
+//   - Jacobi smoothing with a Chebyshev pair of weights, piecewise-constant prolongation and its transpose as the
 //     restriction, the 5-point operator rediscretised on every level: the cycle is a
 //     symmetric positive-definite operator, as CG needs;
 //   - the cycle runs in float32 (it only steers the search direction; the residual
@@ -30,7 +30,11 @@ constexpr int kMaxIter = 1 << 15;
 constexpr int kCheckEvery = 8;
 constexpr int kBlock = 256;
 constexpr int kMaxLevels = 20;
-constexpr float kOmega = 0.8f;
+constexpr float kOmega = 0.8f;     // damped Jacobi on the coarsest level
+// The two sweeps of a V-cycle leg use the degree-2 Chebyshev weights for the high-frequency band
+// [0.5, 2] of D^-1 A (smoothing factor 0.22 per leg instead of 0.36 with 0.8, 0.8); the up leg
+// applies them in reverse order, which keeps the cycle symmetric.
+constexpr float kOmegaA = 1.39f, kOmegaB = 0.56f;
 constexpr int kCoarsestSweeps = 8;   // even: the coarsest result lands in Level::y
 
 struct Scalars {          // device-resident, indexed by iteration
@@ -527,16 +531,16 @@ struct TileBuf {
     float b[kHY][kHX];
     float s0[kHY][kHX];
     float s1[kHY][kHX];
-    float dinv[kHY][kHX];   // omega / degree on unknown cells, 0 elsewhere (which also zeroes the iterate there)
+    float dinv[kHY][kHX];   // 1 / degree on unknown cells, 0 elsewhere (which also zeroes the iterate there)
     float deg[kHY][kHX];
 };
 
 // x + omega (b - A x) / deg, with x == 0 off the unknown set (dinv == 0 there keeps it so)
-__device__ __forceinline__ float jacobi(const float (*x)[kHX], const TileBuf& t, int ly, int lx) {
+__device__ __forceinline__ float jacobi(const float (*x)[kHX], const TileBuf& t, int ly, int lx, float omega) {
     const float xi = x[ly][lx];
     const float s = x[ly - 1][lx] + x[ly + 1][lx] + x[ly][lx - 1] + x[ly][lx + 1];
     const float dv = t.dinv[ly][lx];
-    return dv == 0.f ? 0.f : xi + dv * (t.b[ly][lx] - (t.deg[ly][lx] * xi - s));
+    return dv == 0.f ? 0.f : xi + omega * dv * (t.b[ly][lx] - (t.deg[ly][lx] * xi - s));
 }
 
 // Thread mapping of the fused legs: thread t owns column lx = t & 63 of the halo'd tile and the
@@ -593,19 +597,19 @@ __device__ __forceinline__ void load_tile(TileBuf& t, const TilePos& p, const fl
         if (mm[e]) {
             const int d = p.dxh + ((y > 0) || above) + ((y + 1 < ny) || below);
             dg = (float)d;
-            dv = kOmega * __frcp_rn((float)(d > 0 ? d : 1));
-            s = UP ? xv[e] + cv[e] : dv * bb[e];     // down: first sweep from the zero vector
+            dv = __frcp_rn((float)(d > 0 ? d : 1));
+            s = UP ? xv[e] + cv[e] : kOmegaA * dv * bb[e];     // down: first sweep (weight A) from the zero vector
         }
         t.b[ly][p.lx] = bb[e]; t.dinv[ly][p.lx] = dv; t.deg[ly][p.lx] = dg; t.s0[ly][p.lx] = s;
     }
 }
 
-__device__ __forceinline__ void sweep_ring1(TileBuf& t, const TilePos& p) {   // s1 = jacobi(s0) on the tile plus one ring
+__device__ __forceinline__ void sweep_ring1(TileBuf& t, const TilePos& p) {   // s1 = jacobi(s0, weight B) on the tile plus one ring
     if (p.lx >= 1 && p.lx <= kTX + 2) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int ly = p.lyb + 4 * e;
-            if (ly >= 1 && ly <= kTY + 2) t.s1[ly][p.lx] = jacobi(t.s0, t, ly, p.lx);
+            if (ly >= 1 && ly <= kTY + 2) t.s1[ly][p.lx] = jacobi(t.s0, t, ly, p.lx, kOmegaB);
         }
     }
 }
@@ -678,7 +682,7 @@ __global__ void __launch_bounds__(kBlock) up_kernel(const float* __restrict__ x,
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int ly = p.lyb + 4 * e, y = p.y_first + 4 * e;
-                if (ly >= 2 && ly < kTY + 2 && y < ny) xout[p.g0 + (int64_t)(4 * e) * nx] = jacobi(t.s1, t, ly, p.lx);
+                if (ly >= 2 && ly < kTY + 2 && y < ny) xout[p.g0 + (int64_t)(4 * e) * nx] = jacobi(t.s1, t, ly, p.lx, kOmegaA);
             }
         }
     }

@@ -227,3 +227,51 @@ def band_experiment2(split=3):
 
 if len(sys.argv) > 1 and sys.argv[1] == 'bands2':
     band_experiment2()
+
+
+def cheb_experiment():
+    """two damped-Jacobi sweeps (0.8, 0.8) vs a degree-2 Chebyshev pair, reversed on the way up"""
+    x, y, z, _ = O.synth_cloud(500000, 500.0, 500.0, seed=0)
+    st = {}
+    O.smrf(x, y, z, 1, 18, .15, .5, 1.25, stages=st)
+
+    class ChebMG(MG):
+        def __init__(self, unk, omegas, **kw):
+            super().__init__(unk, **kw)
+            self.omegas = omegas
+        def sweeps(self, l, x, b, omegas):
+            unk, deg = self.levels[l]
+            for om in omegas:
+                x = x + om * np.where(unk, (b - applyA(x, unk, deg)) / deg, 0.0)
+            return x
+        def vcycle(self, l, b):
+            unk, deg = self.levels[l]
+            if l == len(self.levels) - 1:
+                return self.smooth(l, np.zeros_like(b), b, 8)
+            x = self.sweeps(l, np.zeros_like(b), b, self.omegas)
+            r = np.where(unk, b - applyA(x, unk, deg), 0.0)
+            uc, _ = self.levels[l + 1]
+            ec = self.vcycle(l + 1, np.where(uc, restrict(r, uc.shape), 0.0))
+            x = x + np.where(unk, prolong(ec, unk.shape), 0.0)
+            return self.sweeps(l, x, b, self.omegas[::-1])
+
+    for name in ('Zmin_binned', 'Zpro_punched'):
+        G = st[name]
+        unk = np.isnan(G); deg = deg_of(unk.shape)
+        for omegas in ((0.8, 0.8), (1.39, 0.56), (0.56, 1.39), (1.3, 0.6), (1.2, 0.65), (1.0, 0.7)):
+            mg = ChebMG(unk, omegas)
+            u = np.where(unk, np.nanmean(G), G)
+            s = np.zeros_like(u)
+            s[1:, :] += u[:-1, :]; s[:-1, :] += u[1:, :]; s[:, 1:] += u[:, :-1]; s[:, :-1] += u[:, 1:]
+            r = np.where(unk, s - deg * u, 0.0)
+            zz = mg.vcycle(0, r); p = zz.copy(); rz = (r * zz).sum(); it = 0
+            while np.abs(r).max() > 1e-7 and it < 300:
+                q = applyA(p, unk, deg); a = rz / (p * q).sum()
+                u += a * p; r -= a * q
+                zz = mg.vcycle(0, r); rz2 = (r * zz).sum()
+                p = zz + (rz2 / rz) * p; rz = rz2; it += 1
+            print(name, omegas, 'iters', it)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == 'cheb':
+    cheb_experiment()
