@@ -5,7 +5,7 @@
 //     deg(i) u_i - sum_{NaN nbrs j} u_j = sum_{known nbrs k} a_k,   deg = in-grid neighbours,
 // a symmetric positive-definite system (per connected NaN region that touches a known
 // cell).  Here it is solved by conjugate gradients in float64 whose every vector lives in
-// HBM, preconditioned by one geometric multigrid V(2,2)-cycle per iteration:
+// HBM, preconditioned by one geometric multigrid V(3,3)-cycle per iteration:
 //   - cell-centred 2x2 coarsening; a coarse cell is unknown only if all its children are
 //     (the coarse domains shrink, so Dirichlet data never leaks into a correction);
 //   - Jacobi smoothing with a Chebyshev pair of weights, piecewise-constant prolongation and its transpose as the
@@ -31,10 +31,10 @@ constexpr int kCheckEvery = 8;
 constexpr int kBlock = 256;
 constexpr int kMaxLevels = 20;
 constexpr float kOmega = 0.8f;     // damped Jacobi on the coarsest level
-// The two sweeps of a V-cycle leg use the degree-2 Chebyshev weights for the high-frequency band
-// [0.5, 2] of D^-1 A (smoothing factor 0.22 per leg instead of 0.36 with 0.8, 0.8); the up leg
+// The three sweeps of a V-cycle leg use the degree-3 Chebyshev weights for the high-frequency band
+// [0.5, 2] of D^-1 A (smoothing factor 0.074 per leg; two sweeps with 0.8 give 0.36); the up leg
 // applies them in reverse order, which keeps the cycle symmetric.
-constexpr float kOmegaA = 1.39f, kOmegaB = 0.56f;
+constexpr float kOmegaA = 1.6653f, kOmegaB = 0.8f, kOmegaC = 0.5265f;
 constexpr int kCoarsestSweeps = 8;   // even: the coarsest result lands in Level::y
 
 struct Scalars {          // device-resident, indexed by iteration
@@ -520,12 +520,13 @@ __global__ void __launch_bounds__(kBlock) prolong_kernel(float* __restrict__ x, 
 }
 
 // ---- fused legs of the V-cycle: each level is two launches and two passes over its vectors ----
-// A CTA owns a 28 x 60 tile; everything a sweep needs from neighbours is recomputed in a
-// two-cell halo held in shared memory (temporal blocking of the two Jacobi sweeps).  The
-// halo'd tile is 32 x 64 so that local indices are shifts and masks; the in-grid test, the
-// mask and 1/degree are evaluated once per element while loading.
-constexpr int kTY = 28, kTX = 60;
+// A CTA owns a 26 x 58 tile; everything its three sweeps need from neighbours is recomputed in a
+// three-cell halo held in shared memory (temporal blocking of the Jacobi sweeps).  The halo'd
+// tile is 32 x 64 so that local indices are shifts and masks; the in-grid test, the mask and
+// 1/degree are evaluated once per element while loading.
+constexpr int kH = 3;                                // sweeps per leg = halo width
 constexpr int kHY = 32, kHX = 64;
+constexpr int kTY = kHY - 2 * kH, kTX = kHX - 2 * kH;
 
 struct TileBuf {
     float b[kHY][kHX];
@@ -557,8 +558,8 @@ __device__ __forceinline__ TilePos tile_pos(int64_t y0, int64_t x0, int64_t nx) 
     TilePos p;
     p.lx = threadIdx.x & 63;
     p.lyb = threadIdx.x >> 6;
-    const int64_t xx = x0 + p.lx - 2;
-    p.y_first = (int)(y0 - 2 + p.lyb);
+    const int64_t xx = x0 + p.lx - kH;
+    p.y_first = (int)(y0 - kH + p.lyb);
     p.col_ok = xx >= 0 && xx < nx;
     p.dxh = (xx > 0) + (xx + 1 < nx);
     p.g0 = (int64_t)p.y_first * nx + xx;
@@ -604,17 +605,21 @@ __device__ __forceinline__ void load_tile(TileBuf& t, const TilePos& p, const fl
     }
 }
 
-__device__ __forceinline__ void sweep_ring1(TileBuf& t, const TilePos& p) {   // s1 = jacobi(s0, weight B) on the tile plus one ring
-    if (p.lx >= 1 && p.lx <= kTX + 2) {
+// dst = jacobi(src, omega) on the tile plus `ring` rings
+template <int RING>
+__device__ __forceinline__ void sweep(float (*dst)[kHX], const float (*src)[kHX], const TileBuf& t, const TilePos& p,
+                                      float omega) {
+    constexpr int lo = kH - RING, hiy = kHY - 1 - (kH - RING), hix = kHX - 1 - (kH - RING);
+    if (p.lx >= lo && p.lx <= hix) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int ly = p.lyb + 4 * e;
-            if (ly >= 1 && ly <= kTY + 2) t.s1[ly][p.lx] = jacobi(t.s0, t, ly, p.lx, kOmegaB);
+            if (ly >= lo && ly <= hiy) dst[ly][p.lx] = jacobi(src, t, ly, p.lx, omega);
         }
     }
 }
 
-// down leg: x = two damped-Jacobi sweeps from zero on A x = b;  bc = P^T (b - A x)
+// down leg: x = three Jacobi sweeps (weights A, B, C) from zero on A x = b;  bc = P^T (b - A x)
 __global__ void __launch_bounds__(kBlock) down_kernel(const float* __restrict__ b, const uint8_t* __restrict__ m,
                                                       float* __restrict__ xout, const uint8_t* __restrict__ mc,
                                                       float* __restrict__ bc, int64_t ny, int64_t nx, int64_t cy,
@@ -628,16 +633,18 @@ __global__ void __launch_bounds__(kBlock) down_kernel(const float* __restrict__ 
         __syncthreads();
         load_tile<false>(t, p, b, m, nullptr, nullptr, (int)ny, nx, 0, above, below);
         __syncthreads();
-        sweep_ring1(t, p);
+        sweep<2>(t.s1, t.s0, t, p, kOmegaB);
         __syncthreads();
-        if (p.col_ok && p.lx >= 2 && p.lx < kTX + 2) {
+        sweep<1>(t.s0, t.s1, t, p, kOmegaC);
+        __syncthreads();
+        if (p.col_ok && p.lx >= kH && p.lx < kTX + kH) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int ly = p.lyb + 4 * e, y = p.y_first + 4 * e;
-                if (ly >= 2 && ly < kTY + 2 && y < ny) xout[p.g0 + (int64_t)(4 * e) * nx] = t.s1[ly][p.lx];
+                if (ly >= kH && ly < kTY + kH && y < ny) xout[p.g0 + (int64_t)(4 * e) * nx] = t.s0[ly][p.lx];
             }
         }
-        // coarse right-hand side: 14 x 30 coarse cells per tile
+        // coarse right-hand side: 13 x 29 coarse cells per tile
         for (int i = threadIdx.x; i < (kTY / 2) * 32; i += kBlock) {
             const int cly = i >> 5, clx = i & 31;
             const int64_t Y = y0 / 2 + cly, X = x0 / 2 + clx;
@@ -648,10 +655,10 @@ __global__ void __launch_bounds__(kBlock) down_kernel(const float* __restrict__ 
                     for (int a2 = 0; a2 < 2; ++a2)
 #pragma unroll
                         for (int c2 = 0; c2 < 2; ++c2) {
-                            const int ly = 2 * cly + a2 + 2, lx = 2 * clx + c2 + 2;
+                            const int ly = 2 * cly + a2 + kH, lx = 2 * clx + c2 + kH;
                             if (t.dinv[ly][lx] != 0.f) {
-                                const float sum = t.s1[ly - 1][lx] + t.s1[ly + 1][lx] + t.s1[ly][lx - 1] + t.s1[ly][lx + 1];
-                                acc += t.b[ly][lx] - (t.deg[ly][lx] * t.s1[ly][lx] - sum);
+                                const float sum = t.s0[ly - 1][lx] + t.s0[ly + 1][lx] + t.s0[ly][lx - 1] + t.s0[ly][lx + 1];
+                                acc += t.b[ly][lx] - (t.deg[ly][lx] * t.s0[ly][lx] - sum);
                             }
                         }
                 }
@@ -661,8 +668,8 @@ __global__ void __launch_bounds__(kBlock) down_kernel(const float* __restrict__ 
     }
 }
 
-// up leg: x += P xc, then two damped-Jacobi sweeps; written to `xout` (another buffer: tiles read
-// each other's halo of x)
+// up leg: x += P xc, then three Jacobi sweeps (weights C, B, A: the down leg's in reverse, which
+// keeps the cycle symmetric); written to `xout` (another buffer: tiles read each other's halo of x)
 __global__ void __launch_bounds__(kBlock) up_kernel(const float* __restrict__ x, const float* __restrict__ xc,
                                                     const float* __restrict__ b, const uint8_t* __restrict__ m,
                                                     float* __restrict__ xout, int64_t ny, int64_t nx, int64_t cx,
@@ -676,13 +683,15 @@ __global__ void __launch_bounds__(kBlock) up_kernel(const float* __restrict__ x,
         __syncthreads();
         load_tile<true>(t, p, b, m, x, xc, (int)ny, nx, cx, above, below);
         __syncthreads();
-        sweep_ring1(t, p);
+        sweep<2>(t.s1, t.s0, t, p, kOmegaC);
         __syncthreads();
-        if (p.col_ok && p.lx >= 2 && p.lx < kTX + 2) {
+        sweep<1>(t.s0, t.s1, t, p, kOmegaB);
+        __syncthreads();
+        if (p.col_ok && p.lx >= kH && p.lx < kTX + kH) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int ly = p.lyb + 4 * e, y = p.y_first + 4 * e;
-                if (ly >= 2 && ly < kTY + 2 && y < ny) xout[p.g0 + (int64_t)(4 * e) * nx] = jacobi(t.s1, t, ly, p.lx, kOmegaA);
+                if (ly >= kH && ly < kTY + kH && y < ny) xout[p.g0 + (int64_t)(4 * e) * nx] = jacobi(t.s0, t, ly, p.lx, kOmegaA);
             }
         }
     }

@@ -35,7 +35,7 @@ SPLINE_HALO = 80
 
 # ------------------------------------------------------------------ partition + halo helpers
 MG_SPLIT = 3          # multigrid levels 0..2 run on the (ghost-extended) band, level 3 and coarser on the global grid
-MG_GHOST = 48         # ghost rows per side for those levels: a multiple of 2**MG_SPLIT, >= their dependency radius (~37)
+MG_GHOST = 64         # ghost rows per side for those levels: a multiple of 2**MG_SPLIT, >= their dependency radius (~52)
 
 
 def rows_per_band(ny, world):

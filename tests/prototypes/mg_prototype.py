@@ -258,7 +258,7 @@ def cheb_experiment():
     for name in ('Zmin_binned', 'Zpro_punched'):
         G = st[name]
         unk = np.isnan(G); deg = deg_of(unk.shape)
-        for omegas in ((0.8, 0.8), (1.39, 0.56), (0.56, 1.39), (1.3, 0.6), (1.2, 0.65), (1.0, 0.7)):
+        for omegas in ((0.8, 0.8), (1.39, 0.56), (1.6653, 0.8, 0.5265), (0.5265, 0.8, 1.6653), (1.39, 0.56, 1.39, 0.56), (1.771, 1.0, 0.6393, 0.5122)):
             mg = ChebMG(unk, omegas)
             u = np.where(unk, np.nanmean(G), G)
             s = np.zeros_like(u)
