@@ -475,50 +475,6 @@ __global__ void __launch_bounds__(kBlock) smooth_kernel(const float* __restrict_
     }
 }
 
-// bc = P^T (b - A x): the sum of the residuals of the (up to four) children
-__global__ void __launch_bounds__(kBlock) restrict_kernel(const float* __restrict__ x, const float* __restrict__ b,
-                                                          const uint8_t* __restrict__ mc, float* __restrict__ bc,
-                                                          int64_t fy, int64_t fx, int64_t cy, int64_t cx, int above,
-                                                          int below) {
-    const Tiles T(cy, cx);
-    SMRF_FOR_TILES(T, Y, X, in) {
-        if (in) {
-            float acc = 0.f;
-            if (mc[Y * cx + X]) {      // all children unknown
-#pragma unroll
-                for (int a = 0; a < 2; ++a)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int64_t y = 2 * Y + a, xx = 2 * X + c;
-                        if (y < fy && xx < fx) {
-                            const int64_t i = y * fx + xx;
-                            float s = 0.f;
-                            if (y > 0) s += x[i - fx];
-                            if (y + 1 < fy) s += x[i + fx];
-                            if (xx > 0) s += x[i - 1];
-                            if (xx + 1 < fx) s += x[i + 1];
-                            acc += b[i] - ((float)degree(y, xx, fy, fx, above, below) * x[i] - s);
-                        }
-                    }
-            }
-            bc[Y * cx + X] = acc;
-        }
-    }
-}
-
-// x += P xc on the unknown fine cells
-__global__ void __launch_bounds__(kBlock) prolong_kernel(float* __restrict__ x, const float* __restrict__ xc,
-                                                         const uint8_t* __restrict__ m, int64_t fy, int64_t fx,
-                                                         int64_t cx) {
-    const Tiles T(fy, fx);
-    SMRF_FOR_TILES(T, y, xx, in) {
-        if (in) {
-            const int64_t i = y * fx + xx;
-            if (m[i]) x[i] += xc[(y >> 1) * cx + (xx >> 1)];
-        }
-    }
-}
-
 // ---- fused legs of the V-cycle: each level is two launches and two passes over its vectors ----
 // A CTA owns a 26 x 58 tile; everything its three sweeps need from neighbours is recomputed in a
 // three-cell halo held in shared memory (temporal blocking of the Jacobi sweeps).  The halo'd
@@ -860,8 +816,6 @@ int smrf_inpaint_start(const void* grid, int64_t ny, int64_t nx, int dtype, void
     const int64_t n = ny * nx;
     if (phase == 0) {   // u = known value or the starting guess (the caller exchanges boundary rows of u next)
         // init_u_kernel reads the guess from the statistics block: store it there as a mean over one cell
-        Scalars tmp_stats;
-        (void)tmp_stats;
         double g = guess;
         unsigned long long one = 1;
         SMRF_CUDA(cudaMemcpyAsync(&w.sc->sum_known, &g, 8, cudaMemcpyHostToDevice, st));
