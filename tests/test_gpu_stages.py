@@ -74,6 +74,17 @@ def test_create_dem_edge_rule_nan_z_and_errors(nb):
     assert not np.isnan(Ii).any()
 
 
+def test_create_dem_with_explicit_edges(nb):
+    """edges=(xedges, yedges): points outside are dropped first (neilpy.py:1125-1132), cellsize comes from the edges"""
+    x, y, z, _ = O.synth_cloud(100000, 300.0, 200.0, seed=8, dtype=np.float64)
+    xedges = np.arange(40.0, 261.0, 2.0)
+    yedges = np.arange(170.0, 29.0, -2.0)
+    for bin_type in ('min', 'max'):
+        I0, t0 = O.create_dem(x, y, z, cellsize=1, bin_type=bin_type, edges=(xedges, yedges))
+        I1, t1 = nb.create_dem(x, y, z, cellsize=1, bin_type=bin_type, edges=(xedges, yedges))
+        assert tuple(t1)[:6] == t0.coeffs and eq_nan(I0, I1) and I1.shape == (len(yedges) - 1, len(xedges) - 1)
+
+
 # ------------------------------------------------------------------ progressive_filter
 def surface(ny, nx, seed, dtype=np.float64):
     rng = np.random.default_rng(seed)
