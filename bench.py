@@ -64,8 +64,16 @@ class ClockSampler:
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
+    """`nvidia-smi -lms 20` in its own process.  It is started BEFORE the warm-up steps -- its NVML
+    start-up stalls CUDA launches for tens of milliseconds -- and only the rows stamped inside the timed
+    region (`window(t0, t1)`) are reported."""
+
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def start(self):
         try:
@@ -79,7 +87,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
 
     def stop(self):
         if not self.proc:
@@ -92,7 +100,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.t0 is not None and not (self.t0 <= ts <= self.t1):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for nme, v in zip(names, r[3:7]):
@@ -275,19 +285,24 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident steps
-    for _ in range(args.warmup):
-        run(pts)
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    for _ in range(args.warmup):
+        Z, t, oc, op = run(pts)         # held like the timed steps' results: the caching allocator reaches its steady state
+    barrier()
+    t_begin = time.perf_counter()
     launches0 = lib.smrf_launch_count() if hasattr(lib, 'smrf_launch_count') else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         Z, t, oc, op = run(pts)
+        marks[i].record()
     e1.record()
     barrier()
+    sampler.window(t_begin, time.perf_counter())
     ms = e0.elapsed_time(e1) / args.steps
+    step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
     launches = (lib.smrf_launch_count() - launches0) if launches0 is not None else None
     clocks = sampler.stop()
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -301,8 +316,7 @@ def run_gpu(args):
     def run_host():
         if world == 1:
             return nb.smrf(host, **PARAMS)              # pinned H2D in, pageable D2H out, inside the API
-        Zd, td, ocd, opd = run(host)                    # H2D inside; this rank's band and point mask come back
-        return Zd.cpu().numpy(), td, ocd.cpu().numpy(), opd.cpu().numpy()
+        return run(host)                                # H2D inside; this rank's band and point mask come back as numpy
     run_host()                                          # warm-up
     barrier()
     t0 = time.perf_counter()
@@ -365,7 +379,7 @@ def run_gpu(args):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args),
-                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu}
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'step_ms': step_ms, 'roofline': roof, 'cpu_baseline': cpu}
         line.update(extra)
     if world > 1:
         dist.barrier()

@@ -305,7 +305,8 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     """`neilpy.smrf` (neilpy.py:1685-1808) over all ranks of `group`.
 
     points : this rank's slice of the cloud, an (N, 4) float32 CUDA tensor (x, y, z, unused)
-             or a tuple (x, y, z) of equal-length CUDA tensors.
+             or a tuple (x, y, z) of equal-length CUDA tensors.  Host arrays / tensors are
+             accepted too (copied in; the grids and the point mask then come back as numpy).
     Returns a dict: 'Zpro' / 'object_cells' (this rank's row band, or the full grids on
     every rank if gather=True), 'rows' (the band's global row range), 't' (the transform),
     'is_object_point' (for this rank's points), 'shape' (global ny, nx), 'info'.
@@ -443,4 +444,7 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
         res['Zpro'], res['object_cells'] = full(Zpro, 0), full(object_cells, 0).view(torch.bool)
     else:
         res['Zpro'], res['object_cells'] = Zpro, object_cells.view(torch.bool)
+    if not pts.on_device:                                # host points in -> numpy out, like api.smrf
+        for k in ('Zpro', 'object_cells', 'is_object_point'):
+            res[k] = api._to_host(res[k])
     return res

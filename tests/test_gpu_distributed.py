@@ -33,7 +33,15 @@ def _worker(rank, world, port, q):
         mine = torch.as_tensor(xyzw[rank::world].copy()).cuda()           # an arbitrary slice of the cloud
         res = smrf_sharded(mine, gather=True, **kw)
         ok, msg = True, ''
-        if rank == 0:
+        # host points in -> numpy out (the band only), same values as the device call
+        resh = smrf_sharded(xyzw[rank::world].copy(), **kw)
+        r0, r1 = resh['rows']
+        ok_host = (isinstance(resh['Zpro'], np.ndarray) and resh['object_cells'].dtype == np.bool_
+                   and np.allclose(resh['Zpro'], res['Zpro'][r0:r1].cpu().numpy(), atol=1e-6)
+                   and int((resh['is_object_point'] != res['is_object_point'].cpu().numpy()).sum()) <= 2)
+        if not ok_host:
+            ok, msg = False, 'host-input call differs from the device call on rank %d' % rank
+        if rank == 0 and ok:
             Z1, t1, oc1, op1 = nb.smrf(torch.as_tensor(xyzw).cuda(), **kw)
             dz = float((res['Zpro'] - Z1).abs().max())
             cf = int((res['object_cells'] != oc1).sum())
