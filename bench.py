@@ -375,6 +375,11 @@ def run_gpu(args):
                 extra['opening_c3'] = opening_c3(torch, nb, dev, peaks, args.c3)
             except Exception as e:                       # noqa: BLE001  (report, do not hide the main line)
                 extra['opening_c3'] = {'error': repr(e)}
+        if world == 1:
+            try:
+                extra['las_decode'] = las_decode_leg(torch, dev, peaks, args.points)
+            except Exception as e:                       # noqa: BLE001
+                extra['las_decode'] = {'error': repr(e)}
         cpu = cpu_baseline_leg(args.cpu_points) if (world == 1 and args.cpu_points > 0) else None
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak',
@@ -386,6 +391,30 @@ def run_gpu(args):
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def las_decode_leg(torch, dev, peaks, n, fmt=1):
+    """The step before the path: n LAS records of point format 1 (28 packed
+    bytes) resident in HBM -> x, y, z float64 columns + the classification byte.  Algorithmic bytes
+    per point: record + 3*8 + 1."""
+    from neilpy_b200 import las
+    length = las.RECORD_LENGTH[fmt]
+    records = torch.randint(0, 256, (n * length,), dtype=torch.uint8, device=dev)
+    scale, offset = (0.01, 0.01, 0.01), (500000.0, 5400000.0, 0.0)
+    las.decode_records(records, n, fmt, scale, offset)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        out = las.decode_records(records, n, fmt, scale, offset)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps                       # includes torch.empty of the four outputs (cached blocks)
+    gbs = n * (length + 25) / (ms * 1e-3) / 1e9
+    del out, records
+    return {'format': fmt, 'record_bytes': length, 'points': n, 'ms': ms, 'points_per_s': n / (ms * 1e-3),
+            'achieved_GBs': gbs, 'frac': gbs / peaks['hbm_gbs'], 'algorithmic_bytes_per_point': length + 25}
 
 
 def opening_c3(torch, nb, dev, peaks, n):

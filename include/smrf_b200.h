@@ -231,6 +231,25 @@ int smrf_classify(const void* x, const void* y, const void* z, int64_t n, int po
                   uint8_t* is_object, double* elevation, double* slope_out,
                   const uint8_t* drop_raster, uint8_t* when_dropped_pt, void* stream);
 
+/* ---- LAS ingest / egress (the step before and after the path) -- neilpy.py:903-1087
+ * `records` is the point-data block of a LAS file as it lies in the file (packed records of
+ * `record_length` bytes, little-endian, X Y Z int32 first), copied to the device at a
+ * 16-byte aligned address.  smrf_las_decode writes x = X*scale[0] + offset[0] etc. as float64
+ * (product rounded, then sum rounded: neilpy.py:1056-1059) and, if `classification` is not
+ * NULL, the raw byte at `class_offset` of every record (the reference's 'class' column:
+ * offset 15 in point formats 0-5, 16 in formats 6-10).  scale3/offset3 are HOST arrays of
+ * three doubles.  record_length 12..200. */
+int smrf_las_decode(const uint8_t* records, int64_t n, int record_length, const double* scale3_host,
+                    const double* offset3_host, double* x, double* y, double* z, uint8_t* classification,
+                    int class_offset, void* stream);
+/* classification byte of record i = (old & keep_mask) | (is_object_point[i] ? object_code :
+ * ground_code), in place.  The reference's laspy notebook writes 2*(1-is_object_point)
+ * (examples/smrf/SMRF Classification using laspy to read and write.ipynb, cell 5): ground 2,
+ * object 0; keep_mask 0xE0 preserves the flag bits that share the byte in formats 0-5, 0 in
+ * formats 6-10. */
+int smrf_las_write_class(uint8_t* records, int64_t n, int record_length, int class_offset, int keep_mask,
+                         const uint8_t* is_object_point, int ground_code, int object_code, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

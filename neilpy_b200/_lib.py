@@ -53,6 +53,8 @@ SIGNATURES = {
     'smrf_spline_prefilter': (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     'smrf_classify': (_i32, [_vp, _vp, _vp, _i64, _i32, _dp, _vp, _vp, _i64, _i64, _i32, _dbl, _dbl,
                              _vp, _vp, _vp, _vp, _vp, _vp]),
+    'smrf_las_decode': (_i32, [_vp, _i64, _i32, _dp, _dp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    'smrf_las_write_class': (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),
 }
 
 _lib = None

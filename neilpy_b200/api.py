@@ -20,6 +20,7 @@ metres at which the harmonic solver stops).
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 
 import numpy as np
 import torch
@@ -114,7 +115,9 @@ class _Points:
                 arr = np.asarray(v.values if hasattr(v, 'values') else v)
                 if arr.dtype != np.float32:
                     arr = arr.astype(np.float64, copy=False)
-                t = torch.from_numpy(np.ascontiguousarray(arr))
+                with warnings.catch_warnings():           # read-only views (pandas copy-on-write) are only read here
+                    warnings.simplefilter('ignore', UserWarning)
+                    t = torch.from_numpy(np.ascontiguousarray(arr))
             ts.append(t.reshape(-1))
         self.on_device = all(t.is_cuda for t in ts)
         if all(t.dtype == torch.float32 for t in ts):
