@@ -380,6 +380,11 @@ def run_gpu(args):
                 extra['las_decode'] = las_decode_leg(torch, dev, peaks, args.points)
             except Exception as e:                       # noqa: BLE001
                 extra['las_decode'] = {'error': repr(e)}
+        if world == 1:
+            try:
+                extra['terrain'] = terrain_leg(torch, Z)
+            except Exception as e:                       # noqa: BLE001
+                extra['terrain'] = {'error': repr(e)}
         cpu = cpu_baseline_leg(args.cpu_points) if (world == 1 and args.cpu_points > 0) else None
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak',
@@ -415,6 +420,25 @@ def las_decode_leg(torch, dev, peaks, n, fmt=1):
     del out, records
     return {'format': fmt, 'record_bytes': length, 'points': n, 'ms': ms, 'points_per_s': n / (ms * 1e-3),
             'achieved_GBs': gbs, 'frac': gbs / peaks['hbm_gbs'], 'algorithmic_bytes_per_point': length + 25}
+
+
+def terrain_leg(torch, Z):
+    """The step after the path: pssm index and hillshade of the step's own DTM, device in / device out."""
+    from neilpy_b200 import terrain
+    out = {'grid': list(Z.shape)}
+    for name, fn in (('pssm_index_ms', lambda: terrain.pssm(Z, cellsize=1, apply_colormap=False)),
+                     ('pssm_rgba_ms', lambda: terrain.pssm(Z, cellsize=1)),
+                     ('hillshade_ms', lambda: terrain.hillshade(Z, cellsize=1))):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / 3
+    return out
 
 
 def opening_c3(torch, nb, dev, peaks, n):

@@ -250,6 +250,28 @@ int smrf_las_decode(const uint8_t* records, int64_t n, int record_length, const 
 int smrf_las_write_class(uint8_t* records, int64_t n, int record_length, int class_offset, int keep_mask,
                          const uint8_t* is_object_point, int ground_code, int object_code, void* stream);
 
+/* ---- raster products of the DTM (the step after the path) ------ neilpy.py:456-484,814-867
+ * One pass over `grid` (ny x nx, `dtype`), float64 arithmetic in the reference's order:
+ *   SMRF_TERRAIN_SLOPE      slope(Z, cellsize, z_factor, return_as): gradient spacing
+ *                           `spacing` = cellsize / z_factor; return_as 0 percent, 1 radians,
+ *                           2 degrees -> out_f64                       neilpy.py:456-467
+ *   SMRF_TERRAIN_ASPECT     aspect(Z, return_as, flat_as): unit-spacing gradient, compass
+ *                           bearing, return_as 1 / 2; flat cells = NaN (flat_is_nan) or
+ *                           flat_value -> out_f64                      neilpy.py:471-484
+ *   SMRF_TERRAIN_HILLSHADE  hillshade(Z, cellsize, z_factor, zenith, azimuth): the caller passes
+ *                           cos / sin of the zenith and the azimuth in radians (np.deg2rad);
+ *                           exactly one of out_u8 (return_uint8=True) / out_f64
+ *                                                                      neilpy.py:814-824
+ *   SMRF_TERRAIN_PSSM       pssm(Z, cellsize, ve): index round(255*deg(atan(ve*S))/90) -> out_u8
+ *                           (may be NULL) and / or its colour lut_rgba[index] -> rgba
+ *                           ([ny][nx][4] float64; lut_rgba = 256 x 4 float64 on the device,
+ *                           matplotlib's bone_r or bone)                neilpy.py:846-867
+ * Unused parameters are ignored. */
+enum { SMRF_TERRAIN_SLOPE = 0, SMRF_TERRAIN_ASPECT = 1, SMRF_TERRAIN_HILLSHADE = 2, SMRF_TERRAIN_PSSM = 3 };
+int smrf_terrain(const void* grid, int64_t ny, int64_t nx, int dtype, int mode, int return_as, double spacing,
+                 int flat_is_nan, double flat_value, double cos_zenith, double sin_zenith, double azimuth_rad,
+                 double ve, double* out_f64, uint8_t* out_u8, double* rgba, const double* lut_rgba, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

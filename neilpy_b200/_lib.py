@@ -54,6 +54,7 @@ SIGNATURES = {
     'smrf_classify': (_i32, [_vp, _vp, _vp, _i64, _i32, _dp, _vp, _vp, _i64, _i64, _i32, _dbl, _dbl,
                              _vp, _vp, _vp, _vp, _vp, _vp]),
     'smrf_las_decode': (_i32, [_vp, _i64, _i32, _dp, _dp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    'smrf_terrain': (_i32, [_vp, _i64, _i64, _i32, _i32, _i32, _dbl, _i32, _dbl, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp]),
     'smrf_las_write_class': (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),
 }
 
