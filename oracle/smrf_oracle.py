@@ -24,12 +24,21 @@ restated from their published definitions:
 Everything else (pandas groupby-min, scipy.sparse + lsqr, RectBivariateSpline,
 np.gradient) is called exactly as the reference calls it.
 
-Parity pin: `smrf` on sample_data/samp12.txt with the notebook parameters
-reproduces the reference notebook's printed output (Type I 2.00566304861 %,
-Type II 4.12498595032 %, total 3.09100328095 %, kappa 93.8109576375 %) digit for
-digit -- tests/test_oracle_golden.py.  At every third-party boundary the
-reference's own tests pin nothing; this restatement run in this image is the
-ground truth there ("parity unpinned" per stage, pinned end to end).
+Parity pins (tests/test_oracle_golden.py):
+ 1. `smrf` on sample_data/samp12.txt with the notebook parameters reproduces the
+    reference notebook's printed output (Type I 2.00566304861 %, Type II
+    4.12498595032 %, total 3.09100328095 %, kappa 93.8109576375 %) digit for digit.
+ 2. The reference's OWN source for the five functions above, cut out of
+    neilpy/neilpy.py and executed unmodified in this container with only the three
+    third-party names above supplied (tests/golden/make_reference_exec_golden.py),
+    returns bit for bit what this restatement returns -- DTM, transform, cell mask,
+    point mask, extras, create_dem min / max+inpaint, inpaint, progressive_filter mask
+    and when_dropped -- on samp11, samp12 and two synthetic clouds (digests in
+    tests/golden/reference_exec.json).
+What stays unpinned is only the three third-party restatements themselves (skimage's
+disk / opening, rasterio's from_origin): the reference's tests hold no vector for
+them and the packages are absent; they follow the packages' published definitions,
+and pin 1 passes through all three.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this module.  The product (neilpy_b200) never does.
