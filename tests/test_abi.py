@@ -63,3 +63,26 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/smrf_b200.h is a C header (no C++ or torch types in the signatures): a C99 program
+    includes it, links the library and calls an entry point that needs no GPU."""
+    import shutil
+    import subprocess
+    from neilpy_b200 import _lib
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    src = tmp_path / 'abi.c'
+    src.write_text('#include "smrf_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %s\\n", smrf_abi_version(), smrf_open_variant(SMRF_F32, 18));'
+                   ' return smrf_abi_version() == 1 ? 0 : 1; }\n')
+    exe = tmp_path / 'abi'
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', os.path.join(ROOT, 'include'),
+                    str(src), '-L', libdir, '-lsmrf_b200', '-Wl,-rpath,' + libdir, '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == '1' and out[1].startswith('march')
