@@ -102,3 +102,20 @@ def test_synthetic_cloud_is_deterministic_and_f32_exact():
     assert np.array_equal(x.astype(np.float32).astype(np.float64), x)
     assert np.array_equal(z.astype(np.float32).astype(np.float64), z)
     assert 0.05 < lab.mean() < 0.6
+
+
+def test_threaded_host_copy(monkeypatch):
+    """The staging -> result copy of api._to_host: exact for every size and dtype, and it picks its
+    own thread count (torchrun exports OMP_NUM_THREADS=1, which would serialise torch's copy)."""
+    from neilpy_b200 import api
+    rng = np.random.default_rng(0)
+    for dt in (np.float32, np.float64, np.uint8, np.bool_):
+        for n in (0, 1, 4097, (4 << 20) + 3):
+            src = rng.integers(0, 2, n).astype(dt)
+            dst = np.empty(n, dt)
+            api._threaded_copy(dst, src)
+            assert np.array_equal(dst, src)
+    monkeypatch.setenv('LOCAL_WORLD_SIZE', '1')
+    one = api._copy_threads()
+    monkeypatch.setenv('LOCAL_WORLD_SIZE', '64')
+    assert 1 <= api._copy_threads() <= one <= 4
