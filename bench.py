@@ -151,12 +151,18 @@ def run_reference(args):
                 times.append(dt)
     ms = 1000.0 * float(np.mean(times))
     value = workers * n / (ms / 1000.0)
-    sample = ('%d independent synthetic clouds of %d points (%.0f m square, 2 pts/m^2), one per worker process, '
-              'oracle smrf cellsize=1 windows=18' % (workers, n, extent_for(n)[0]))
+    sample = ('%d independent synthetic clouds of %d points each (%.0f m square, 2 pts/m^2, cellsize=1, windows=18), one per '
+              'worker process: a CROP of the workload of the GPU arm (the full 50 M-point cloud would take the single-threaded '
+              'reference ~15 min per step)' % (workers, n, extent_for(n)[0]))
+    cfg = workload_config(args)
+    cfg['workload'] = ('CROP of BASELINE.json configs[1] for the CPU reference: %d x %d-point clouds (same generator, density, '
+                       'cellsize=1, windows=18) instead of one %d-point cloud per GPU' % (workers, n, args.points))
+    cfg['points_per_cloud'] = n
+    cfg['clouds_per_step'] = workers
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup_ref, 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args),
+            'config': cfg,
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': workers, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -312,7 +318,7 @@ def run_gpu(args):
     value = world * args.points / (ms_max * 1e-3)
 
     # ---- end to end through the public API with host buffers
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(10, args.steps) if world == 1 else max(5, min(args.steps, 10))
     def run_host():
         if world == 1:
             return nb.smrf(host, **PARAMS)              # pinned H2D in, pageable D2H out, inside the API
@@ -354,6 +360,8 @@ def run_gpu(args):
         sharded_open = {'mcells_per_s': float(cells.item()) / (float(tms.item()) * 1e-3) / 1e6,
                         'ms': float(tms.item()), 'cells': float(cells.item())}
 
+    parity = parity_block(torch, nb, dev, rank, world, args.parity_points)
+
     line = None
     if rank == 0:
         # ---- roofline of the opening kernels on this workload's grid, and the C3 opening-only figure
@@ -389,13 +397,66 @@ def run_gpu(args):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args),
-                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'step_ms': step_ms, 'roofline': roof, 'cpu_baseline': cpu}
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'step_ms': step_ms, 'roofline': roof, 'cpu_baseline': cpu,
+                'parity': parity}
         line.update(extra)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def parity_block(torch, nb, dev, rank, world, n):
+    """Outside the timed region: the row-band sharded path against the unsharded one on the same
+    sub-cloud (n points, the workload's generator and density).  At N > 1 the N real ranks run
+    `smrf_sharded` over NCCL and rank 0 also runs `neilpy_b200.smrf` on the whole sub-cloud; at N = 1
+    four virtual bands (threads of this process, neilpy_b200.comm.ThreadComm) run the same band code.
+    Reports flips, max |dZ|, CG iteration counts and sha256 digests of the masks."""
+    import hashlib
+    from neilpy_b200.distributed import smrf_sharded
+    from neilpy_b200.comm import run_virtual_ranks
+    from neilpy_b200.synth import synth_cloud
+    if n <= 0:
+        return None
+    bands = world if world > 1 else 4
+    side = float(np.sqrt(n / DENSITY))
+    x, y, z, _ = synth_cloud(n, side, side, seed=12345)
+    xyzw = np.stack([x, y, z, np.zeros_like(x)], 1).astype(np.float32)
+    sha = lambda t: hashlib.sha256(np.packbits(t.cpu().numpy().astype(bool))).hexdigest()[:16]
+    if world > 1:
+        res = smrf_sharded(torch.from_numpy(xyzw[rank::world].copy()).to(dev), gather=True, **PARAMS)
+        import torch.distributed as dist
+        mine = res['is_object_point']
+        lens = [len(range(r, n, world)) for r in range(world)]
+        pad = torch.zeros(max(lens), dtype=torch.uint8, device=dev)
+        pad[:mine.numel()] = mine.view(torch.uint8)
+        allm = torch.empty(world * max(lens), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allm, pad)
+        op = torch.empty(n, dtype=torch.bool, device=dev)
+        for r in range(world):
+            op[r::world] = allm[r * max(lens):r * max(lens) + lens[r]].view(torch.bool)
+        results = [res]
+    else:
+        parts = [torch.from_numpy(xyzw[r::bands].copy()).to(dev) for r in range(bands)]
+        results = run_virtual_ranks(bands, lambda comm: smrf_sharded(parts[comm.rank], gather=True, comm=comm, **PARAMS), dev)
+        op = torch.empty(n, dtype=torch.bool, device=dev)
+        for r in range(bands):
+            op[r::bands] = results[r]['is_object_point']
+    if rank != 0:
+        return None
+    st = {}
+    Z1, t1, oc1, op1 = nb.smrf(torch.from_numpy(xyzw).to(dev), return_stages=st, **PARAMS)
+    res = results[0]
+    out = {'what': '%d %s row bands vs the unsharded path, %d-point sub-cloud (%.0f m square)'
+                   % (bands, 'NCCL' if world > 1 else 'virtual (one process, one GPU)', n, side),
+           'grid': list(Z1.shape), 'max_abs_dZ_m': float((res['Zpro'] - Z1).abs().max()),
+           'cell_flips': int((res['object_cells'] != oc1).sum()), 'point_flips': int((op != op1).sum()),
+           'cg_iterations_sharded': [res['info']['inpaint1']['iterations'], res['info']['inpaint2']['iterations']],
+           'cg_iterations_single': [st['inpaint1']['iterations'], st['inpaint2']['iterations']],
+           'sha_point_mask': [sha(op), sha(op1)], 'sha_cell_mask': [sha(res['object_cells']), sha(oc1)]}
+    out['ok'] = bool(out['cell_flips'] == 0 and out['point_flips'] == 0 and out['max_abs_dZ_m'] <= 1e-4)
+    return out
 
 
 def las_decode_leg(torch, dev, peaks, n, fmt=1):
@@ -461,9 +522,10 @@ def main():
     ap.add_argument('--points', type=int, default=50_000_000)
     ap.add_argument('--cpu-points', type=int, default=600_000, help='sample size of the cpu_baseline leg (0 = skip)')
     ap.add_argument('--ref-points', type=int, default=300_000, help='points per worker cloud of --impl reference')
+    ap.add_argument('--parity-points', type=int, default=4_000_000, help='sub-cloud of the sharded-vs-single parity block (0 = skip)')
     ap.add_argument('--c3', type=int, default=32768, help='side of the opening-only grid (BASELINE.json configs[2]; 0 = skip)')
     args = ap.parse_args()
-    args.warmup_ref = min(args.warmup, 1)
+    args.warmup_ref = args.warmup          # the driver's W, also on the reference arm
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -30,7 +30,7 @@ from . import _lib
 from . import spline as _spline
 from .affine import Affine
 
-__all__ = ['smrf', 'create_dem', 'progressive_filter', 'inpaint_nans_by_springs', 'Affine']
+__all__ = ['smrf', 'create_dem', 'progressive_filter', 'inpaint_nans_by_springs', 'Affine', 'InpaintWarning']
 
 INPAINT_TOL = 1e-9       # metres, max-norm of the residual deg*u - sum(nbrs): <= 1e-6 m from the exact fill
 SMRF_INPAINT_TOL = 1e-7  # inside smrf(): <= ~1e-4 m from the exact fill, 100x tighter than the reference's own LSQR
@@ -243,7 +243,23 @@ def _inpaint(lib, grid, ws, tol, unknown=None, guess=None):
     info = (C.c_double * 3)()
     _lib.check(lib.smrf_inpaint(_ptr(grid), ny, nx, _code(grid.dtype), _ptr(unknown), _ptr(guess), _ptr(ws), ws.numel(),
                                 float(tol), INPAINT_MAX_ITER, info, _stream()), 'smrf_inpaint')
-    return {'iterations': int(info[0]), 'residual': float(info[1]), 'unknown': int(info[2])}
+    return _converged({'iterations': int(info[0]), 'residual': float(info[1]), 'unknown': int(info[2])}, tol)
+
+
+class InpaintWarning(RuntimeWarning):
+    """The harmonic solver stopped above its tolerance (iteration cap, or a non-finite residual
+    caused by non-finite elevations).  The reference's LSQR reports nothing in that case either,
+    but a silently unconverged DTM would flow into the classification."""
+
+
+def _converged(info, tol):
+    r = info['residual']
+    info['converged'] = bool(info['unknown'] == 0 or (np.isfinite(r) and r <= tol))
+    if not info['converged']:
+        warnings.warn('inpaint_nans_by_springs: residual %.3g m after %d iterations (tolerance %.3g m)%s'
+                      % (r, info['iterations'], tol, '' if np.isfinite(r) else ' -- non-finite elevations in the grid?'),
+                      InpaintWarning, stacklevel=3)
+    return info
 
 
 def _progressive(lib, surface, windows, thresholds, mask, when, ws, negate=0, last_out=None):

@@ -985,7 +985,7 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
             SMRF_CUDA(cudaMemcpyAsync(&bits, &w.sc->rmax[it], 8, cudaMemcpyDeviceToHost, st));
             SMRF_CUDA(cudaStreamSynchronize(st));
             memcpy(&rmax, &bits, 8);
-            if (!(rmax == rmax)) break;   // NaN: give up rather than spin
+            if (!(rmax < INFINITY)) break;   // NaN / inf: give up rather than spin (the caller reports it)
             const int cap = jacobi ? 64 : kCheckEvery;
             int next = cap;
             if (rmax > tol && rmax > 0.0 && rmax < r_prev && it > it_prev) {

@@ -28,7 +28,8 @@ import math
 
 import numpy as np
 import torch
-import torch.distributed as dist
+
+from .comm import as_comm
 
 SPLINE_HALO = 80
 
@@ -66,25 +67,15 @@ def check_partition(ny, world, halo):
 def exchange_halo(band, h, group=None):
     """Send the first / last `h` rows of `band` ([rows, nx]) to the bands above / below and
     receive theirs.  Returns (above, below): the `h` rows just above band row 0 and just
-    below its last row (None at the global border).  Works for any backend and device."""
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    above = below = None
-    if world == 1 or h == 0:
-        return above, below
+    below its last row (None at the global border).  Works for any backend and device.
+    `group` is a torch.distributed group (None = the default one) or a Comm (neilpy_b200.comm)."""
+    comm = as_comm(group)
+    if comm.world == 1 or h == 0:
+        return None, None
     if band.shape[0] < h:
         raise ValueError('band of %d rows cannot serve a %d-row halo' % (band.shape[0], h))
-    ops = []
-    if rank > 0:
-        above = torch.empty((h,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
-        ops.append(dist.P2POp(dist.isend, band[:h].contiguous(), rank - 1, group))
-        ops.append(dist.P2POp(dist.irecv, above, rank - 1, group))
-    if rank < world - 1:
-        below = torch.empty((h,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
-        ops.append(dist.P2POp(dist.isend, band[-h:].contiguous(), rank + 1, group))
-        ops.append(dist.P2POp(dist.irecv, below, rank + 1, group))
-    for req in dist.batch_isend_irecv(ops):
-        req.wait()
-    return above, below
+    return comm.exchange(band[:h].contiguous() if comm.rank > 0 else None,
+                         band[-h:].contiguous() if comm.rank < comm.world - 1 else None)
 
 
 def with_halo(band, h, group=None):
@@ -92,6 +83,15 @@ def with_halo(band, h, group=None):
     above, below = exchange_halo(band, h, group)
     parts = [t for t in (above, band, below) if t is not None]
     return (torch.cat(parts, 0) if len(parts) > 1 else band), (h if above is not None else 0)
+
+
+def raise_together(comm, err, device):
+    """Every rank calls this with its own exception (or None); if any rank failed, all raise, so a
+    failure on one rank cannot leave the others blocked in a collective."""
+    flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=device)
+    comm.all_reduce(flag, 'max')
+    if int(flag.item()):
+        raise err if err is not None else RuntimeError('another rank of the sharded smrf failed')
 
 
 # ------------------------------------------------------------------ device stages
@@ -103,7 +103,8 @@ def _api():
 def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None, r0=None):
     """Distributed multigrid-preconditioned CG on a row band (see module docstring)."""
     _lib, api = _api()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    comm = group = as_comm(group)
+    rank, world = comm.rank, comm.world
     ny, nx = band.shape
     code = api._code(band.dtype)
     st = api._stream
@@ -124,7 +125,7 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
 
     _lib.check(lib.smrf_inpaint_setup(api._ptr(band), ny, nx, code, wp, wn, ha, hb, st()), 'smrf_inpaint_setup')
     stats = torch.stack([f64(off_stats, 1)[0], i64(off_stats + 8, 2)[0].double(), i64(off_stats + 8, 2)[1].double()])
-    dist.all_reduce(stats, group=group)
+    comm.all_reduce(stats)
     s_known, n_known, n_unknown = [float(v) for v in stats.cpu()]
     info = {'iterations': 0, 'residual': 0.0, 'unknown': int(n_unknown)}
     if n_unknown == 0:
@@ -155,9 +156,9 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
             mine_m = torch.zeros((perL, nxL), dtype=torch.uint8, device=band.device)
             mine_m[:nyL] = wsE[e_mL:e_mL + nyLE * nxL].view(nyLE, nxL)[tL:tL + nyL]
             all_m = torch.empty((perL * world, nxL), dtype=torch.uint8, device=band.device)
-            dist.all_gather_into_tensor(all_m, mine_m, group=group)
+            comm.all_gather(all_m, mine_m)
             tot = torch.tensor([nyL], dtype=torch.int64, device=band.device)
-            dist.all_reduce(tot, group=group)
+            comm.all_reduce(tot)
             nyG = int(tot.item())                      # rows of the global level-MG_SPLIT grid (bands stack without gaps)
             wsC = torch.empty(lib.smrf_inpaint_workspace_bytes(nyG, nxL), dtype=torch.uint8, device=band.device)
             _lib.check(lib.smrf_mg_setup_mask(api._ptr(all_m), nyG, nxL, api._ptr(wsC), wsC.numel(), st()), 'smrf_mg_setup_mask')
@@ -189,7 +190,7 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
         wE, nE = api._ptr(e['ws']), e['ws'].numel()
         _lib.check(lib.smrf_mg_cycle_part(e['nyE'], nx, wE, nE, e['haE'], e['hbE'], MG_SPLIT, 0, st()), 'mg down')
         e['mine'][:e['nyL']] = e['bLE'][e['tL']:e['tL'] + e['nyL']]
-        dist.all_gather_into_tensor(e['full'], e['mine'], group=group)
+        comm.all_gather(e['full'], e['mine'])
         e['cb'].copy_(e['full'][:e['nyG']])
         _lib.check(lib.smrf_mg_vcycle(e['nyG'], e['nxL'], api._ptr(e['wsC']), e['wsC'].numel(), st()), 'smrf_mg_vcycle')
         e['yLE'].copy_(e['cy'][e['g0']:e['g0'] + e['nyLE']])
@@ -202,7 +203,7 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
                                       api._ptr(u_below), st()), 'start1')
 
     def residual(k):
-        dist.all_reduce(rmax[k:k + 1], op=dist.ReduceOp.MAX, group=group)
+        comm.all_reduce(rmax[k:k + 1], 'max')
         return float(rmax[k:k + 1].view(torch.float64).item())
 
     r = residual(0)
@@ -211,16 +212,16 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
         for _ in range(burst):
             k = it
             precondition(k)
-            dist.all_reduce(rz[k:k + 1], group=group)
+            comm.all_reduce(rz[k:k + 1])
             _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 1, z_ptr, None, None, None, None, st()), 'step1')
             p_above, p_below = exchange_halo(p, 1, group)
             _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 2, None, api._ptr(p_above), api._ptr(p_below),
                                              api._ptr(m_above), api._ptr(m_below), st()), 'step2')
-            dist.all_reduce(pq[k:k + 1], group=group)
+            comm.all_reduce(pq[k:k + 1])
             _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 3, None, None, None, None, None, st()), 'step3')
             it += 1
         r = residual(it)
-        if not (r == r):
+        if not math.isfinite(r):
             break
         nxt = 8
         if tol < r < r_prev and it > it_prev:
@@ -230,7 +231,7 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
         r_prev, it_prev, burst = r, it, nxt
     _lib.check(lib.smrf_inpaint_finish(api._ptr(band), ny, nx, code, wp, wn, st()), 'smrf_inpaint_finish')
     info.update(iterations=it, residual=r)
-    return info, ws
+    return api._converged(info, tol), ws
 
 
 def plan_window_chunks(windows, rows, world):
@@ -260,14 +261,15 @@ def _open_windows_band(lib, band, windows, thresholds, mask, when, negate, group
     of the group runs on the extended buffer, its valid row range shrinking by 2w at each
     interior edge (the halo rows are recomputed redundantly instead of being re-exchanged)."""
     _lib, api = _api()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    comm = group = as_comm(group)
+    rank, world = comm.rank, comm.world
     rows, nx = band.shape
     code, st = api._code(band.dtype), api._stream
     cur = band
     last = None
     min_rows = torch.tensor([rows], dtype=torch.int64, device=band.device)
     if world > 1:
-        dist.all_reduce(min_rows, op=dist.ReduceOp.MIN, group=group)
+        comm.all_reduce(min_rows, 'min')
     for chunk in plan_window_chunks([int(w) for w in windows], int(min_rows.item()), world):
         H = sum(2 * int(windows[i]) for i in chunk)
         buf, top = with_halo(cur, H, group)
@@ -301,7 +303,7 @@ def _open_windows_band(lib, band, windows, thresholds, mask, when, negate, group
 
 
 def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_threshold=.5, elevation_scaler=1.25,
-                 low_filter_slope=5, dtype=None, inpaint_tol=None, group=None, gather=False):
+                 low_filter_slope=5, dtype=None, inpaint_tol=None, group=None, gather=False, comm=None):
     """`neilpy.smrf` (neilpy.py:1685-1808) over all ranks of `group`.
 
     points : this rank's slice of the cloud, an (N, 4) float32 CUDA tensor (x, y, z, unused)
@@ -314,7 +316,8 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     _lib, api = _api()
     lib = _lib.load()
     dev = api._device()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    comm = group = as_comm(comm if comm is not None else group)
+    rank, world = comm.rank, comm.world
     import os, time
     timing = {} if os.environ.get('SMRF_TIMING') else None
     t_last = [time.perf_counter()]
@@ -334,19 +337,22 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     tdtype = api._grid_dtype(dtype, pts.default_dtype)
     code, st = api._code(tdtype), api._stream
 
-    # ---- extent: local min/max, then all-reduce
-    out4 = torch.empty(4, dtype=torch.float64, device=dev)
+    # ---- extent: local min/max, then all-reduce (a rank may hold no points at all)
+    out4 = torch.full((4,), float('nan'), dtype=torch.float64, device=dev)
     bad = torch.zeros(1, dtype=torch.int64, device=dev)
-    scratch = torch.empty(4, dtype=torch.int64, device=dev)
-    _lib.check(lib.smrf_extent(pts.ptrs[0], pts.ptrs[1], pts.n, pts.fmt, api._ptr(out4), api._ptr(bad),
-                               api._ptr(scratch), st()), 'smrf_extent')
+    if pts.n:
+        scratch = torch.empty(4, dtype=torch.int64, device=dev)
+        _lib.check(lib.smrf_extent(pts.ptrs[0], pts.ptrs[1], pts.n, pts.fmt, api._ptr(out4), api._ptr(bad),
+                                   api._ptr(scratch), st()), 'smrf_extent')
     lo = torch.stack([out4[0], out4[2]]).nan_to_num(nan=float('inf'))
     hi = torch.stack([out4[1], out4[3]]).nan_to_num(nan=float('-inf'))
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
-    dist.all_reduce(bad, group=group)
-    if int(bad.item()):
-        raise ValueError('x and y must be finite')
+    comm.all_reduce(lo, 'min')
+    comm.all_reduce(hi, 'max')
+    comm.all_reduce(bad)
+    total = torch.tensor([pts.n], dtype=torch.int64, device=dev)
+    comm.all_reduce(total)
+    if int(bad.item()) or int(total.item()) == 0:       # the same on every rank: all raise together
+        raise ValueError('x and y must be finite and non-empty')
     (xmin, ymin), (xmax, ymax) = [float(v) for v in lo.cpu()], [float(v) for v in hi.cpu()]
     xedges, yedges = api._edges(xmin, xmax, ymin, ymax, cellsize)
     nx, ny = len(xedges) - 1, len(yedges) - 1
@@ -363,13 +369,17 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     replica = torch.empty((per * world, nx), dtype=tdtype, device=dev)
     oor = torch.zeros(1, dtype=torch.int64, device=dev)
     _lib.check(lib.smrf_bin_init(api._ptr(replica), per * world, nx, code, _lib.BIN_MIN, st()), 'smrf_bin_init')
-    _lib.check(lib.smrf_bin_accumulate(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, api._ptr(replica),
-                                       ny, nx, code, _lib.BIN_MIN, api._ptr(oor), st()), 'smrf_bin_accumulate')
+    if pts.n:
+        _lib.check(lib.smrf_bin_accumulate(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, api._ptr(replica),
+                                           ny, nx, code, _lib.BIN_MIN, api._ptr(oor), st()), 'smrf_bin_accumulate')
+    comm.all_reduce(oor)
+    if int(oor.item()):                                  # api._bin raises the same (np.ravel_multi_index's message)
+        raise ValueError('invalid entry in coordinates array')
     _lib.check(lib.smrf_bin_finalize_partial(api._ptr(replica), per * world, nx, code, _lib.BIN_MIN, st()),
                'smrf_bin_finalize_partial')
     padded = torch.empty((per, nx), dtype=tdtype, device=dev)
     if world > 1:
-        dist.reduce_scatter_tensor(padded, replica, op=dist.ReduceOp.MIN, group=group)
+        comm.reduce_scatter(padded, replica, 'min')
     else:
         padded.copy_(replica)
     del replica
@@ -422,15 +432,16 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
         del wsp, c, b
     full = torch.empty((per * world, nx, 2), dtype=tdtype, device=dev)
     if world > 1:
-        dist.all_gather_into_tensor(full, mine, group=group)
+        comm.all_gather(full, mine)
     else:
         full.copy_(mine)
     coef = full[:ny]
     mark('slope+spline')
     is_obj = torch.empty(pts.n, dtype=torch.uint8, device=dev)
-    _lib.check(lib.smrf_classify(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, api._ptr(coef),
-                                 None, ny, nx, code, float(elevation_threshold), float(elevation_scaler),
-                                 api._ptr(is_obj), None, None, None, None, st()), 'smrf_classify')
+    if pts.n:
+        _lib.check(lib.smrf_classify(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, api._ptr(coef),
+                                     None, ny, nx, code, float(elevation_threshold), float(elevation_scaler),
+                                     api._ptr(is_obj), None, None, None, None, st()), 'smrf_classify')
     mark('classify')
     res = {'t': t, 'shape': (ny, nx), 'rows': (r0, r1), 'is_object_point': is_obj.view(torch.bool),
            'info': {'inpaint1': info1, 'inpaint2': info2, 'timing_ms': timing}}
@@ -439,7 +450,7 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
             mine = torch.full((per, nx), fill, dtype=band.dtype, device=dev)
             mine[:rows] = band
             out = torch.empty((per * world, nx), dtype=band.dtype, device=dev)
-            dist.all_gather_into_tensor(out, mine, group=group)
+            comm.all_gather(out, mine)
             return out[:ny]
         res['Zpro'], res['object_cells'] = full(Zpro, 0), full(object_cells, 0).view(torch.bool)
     else:

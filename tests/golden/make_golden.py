@@ -27,7 +27,8 @@ sys.path.insert(0, os.path.join(HERE, '..', '..'))
 from oracle import smrf_oracle as O  # noqa: E402
 
 REF = '/root/reference/sample_data'
-SAMPLES = ['samp11', 'samp12', 'samp24', 'samp41', 'samp53', 'samp54']
+SAMPLES = ['samp11', 'samp12', 'samp21', 'samp22', 'samp23', 'samp24', 'samp31', 'samp41', 'samp42', 'samp51',
+           'samp52', 'samp53', 'samp54', 'samp61', 'samp71']     # all 15 of neilpy/test_neilpy.py:61-80
 PARAMS = dict(cellsize=1, windows=18, slope_threshold=.15, elevation_threshold=.5, elevation_scaler=1.25)
 
 

@@ -133,3 +133,44 @@ def test_band_halo_rule_with_two_gloo_ranks():
         p.join(150)
         assert p.exitcode == 0
     assert q.get(timeout=5) == 1
+
+
+def test_thread_comm_collectives_match_their_definitions():
+    """ThreadComm (virtual ranks in one process, neilpy_b200/comm.py) against the definitions the
+    NCCL path relies on: all_reduce, all_gather, reduce_scatter, variable all_to_all, neighbour exchange."""
+    from neilpy_b200.comm import run_virtual_ranks
+    world = 3
+    rng = np.random.default_rng(1)
+    data = [torch.from_numpy(rng.normal(size=(6, 4))) for _ in range(world)]
+    splits = [[1, 2, 3], [0, 4, 2], [3, 3, 0]]        # splits[src][dst]
+
+    def body(comm):
+        r = comm.rank
+        s = comm.all_reduce(data[r].clone(), 'sum')
+        mn = comm.all_reduce(data[r].clone(), 'min')
+        g = comm.all_gather(torch.empty(world * 6, 4, dtype=torch.float64), data[r])
+        rs = comm.reduce_scatter(torch.empty(2, 4, dtype=torch.float64), data[r], 'max')
+        out_splits = [splits[src][r] for src in range(world)]
+        a2a = comm.all_to_all(torch.empty(sum(out_splits), 4, dtype=torch.float64), data[r], out_splits, splits[r])
+        above, below = comm.exchange(data[r][:2] if r > 0 else None, data[r][-2:] if r < world - 1 else None)
+        return s, mn, g, rs, a2a, above, below
+
+    res = run_virtual_ranks(world, body)
+    stack = torch.stack(data)
+    for r, (s, mn, g, rs, a2a, above, below) in enumerate(res):
+        assert torch.equal(s, stack.sum(0)) and torch.equal(mn, stack.amin(0))
+        assert torch.equal(g, torch.cat(data))
+        assert torch.equal(rs, stack.amax(0)[2 * r:2 * r + 2])
+        want = torch.cat([data[src][sum(splits[src][:r]):sum(splits[src][:r + 1])] for src in range(world)])
+        assert torch.equal(a2a, want)
+        assert (above is None) == (r == 0) and (below is None) == (r == world - 1)
+        if r > 0:
+            assert torch.equal(above, data[r - 1][-2:])
+        if r < world - 1:
+            assert torch.equal(below, data[r + 1][:2])
+    with pytest.raises(ValueError):
+        def boom(comm):
+            if comm.rank == 1:
+                raise ValueError('rank 1 failed')
+            comm.barrier()
+        run_virtual_ranks(world, boom)

@@ -40,7 +40,7 @@ def test_samp12_reproduces_notebook_printout(expected):
     assert sha(op) == e['sha_point_mask'] and sha(oc) == e['sha_cell_mask']
 
 
-@pytest.mark.parametrize('name', ['samp24', 'samp54'])
+@pytest.mark.parametrize('name', ['samp21', 'samp24', 'samp31', 'samp54'])
 def test_isprs_regression_pins(expected, name):
     x, y, z, g = load_isprs(name)
     p = expected['params']
