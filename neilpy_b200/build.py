@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, '_build')
 LIB = os.path.join(HERE, 'libsmrf_b200.so')
-MARCH_MAX_W = 40
+MARCH_MAX_W = 72
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC',
@@ -31,10 +31,10 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 
 def _units():
     units = []
-    for name in ('binning', 'grid_ops', 'inpaint', 'spline', 'las', 'terrain', 'opening_generic', 'opening_march'):
+    for name in ('rank', 'binning', 'grid_ops', 'inpaint', 'spline', 'las', 'terrain', 'opening_generic', 'opening_march'):
         units.append((name + '.o', name + '.cu', []))
     for w in range(MARCH_MAX_W, 0, -1):   # slowest first
-        units.append(('opening_march_w%02d.o' % w, 'opening_march_inst.cu', ['-DSMRF_W_LO=%d' % w, '-DSMRF_W_HI=%d' % w]))
+        units.append(('opening_march_w%02d.o' % w, 'opening_march_inst.cu', ['-DSMRF_W=%d' % w]))
     return units
 
 

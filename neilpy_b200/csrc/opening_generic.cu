@@ -103,6 +103,24 @@ int open_window_generic(const void* in, void* out, void* tmp, uint8_t* mask, uin
 
 using namespace smrf;
 
+namespace smrf {
+size_t open_f64_workspace_bytes(int64_t ny, int64_t nx);
+int open_f64_rank(const double* surface, int64_t ny, int64_t nx, int64_t pitch_in, void* ws, size_t ws_bytes, uint8_t* mask,
+                  uint8_t* when, const int32_t* windows, const double* thr, int n_windows, int window_index0, int advance,
+                  int64_t row_lo, int64_t row_hi, double* last_out, int64_t out_pitch, cudaStream_t st);
+}
+
+// float64 surfaces run in rank space (rank.cu) unless every radius is so small that |disk| loads per cell are cheaper
+static bool use_rank_space(int dtype, const int32_t* windows, int n, int negate) {
+    if (dtype != SMRF_F64 || negate || n <= 0 || open_force_generic()) return false;
+    int mx = 0;
+    for (int i = 0; i < n; ++i) {
+        if (windows[i] < 1 || windows[i] > SMRF_MARCH_MAX_W) return false;
+        if (windows[i] > mx) mx = windows[i];
+    }
+    return mx >= 3;
+}
+
 static inline int64_t aligned_pitch(int64_t nx, int dtype) {
     const int64_t q = dtype == SMRF_F64 ? 2 : 4;   // 16-byte rows
     return (nx + q - 1) / q * q;
@@ -114,7 +132,12 @@ size_t smrf_open_workspace_bytes(int64_t ny, int64_t nx, int dtype, int max_wind
     (void)max_window;
     size_t es = dtype == SMRF_F64 ? 8 : 4;
     size_t plane = ((size_t)ny * (size_t)aligned_pitch(nx, dtype) * es + 255) & ~(size_t)255;
-    return 3 * plane;   // two ping-pong surfaces + the erosion intermediate of the generic path
+    size_t need = 3 * plane;   // two ping-pong surfaces + the erosion intermediate (generic path, two-pass radii)
+    if (dtype == SMRF_F64) {   // rank space: sorted table, two float32 rank planes, sort scratch
+        size_t r = open_f64_workspace_bytes(ny, nx);
+        if (r > need) need = r;
+    }
+    return need;
 }
 
 const char* smrf_open_variant(int dtype, int window) {
@@ -133,8 +156,19 @@ int smrf_open_window(const void* in, void* out, void* tmp, uint8_t* mask, uint8_
     SMRF_CHECK_ARG(!when_dropped || mask, "when_dropped needs mask");
     if (row_lo == row_hi) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_rank_space(dtype, &window, 1, negate)) {
+        // float64, one window: rank space with stream-ordered scratch (the one entry point that allocates;
+        // smrf_progressive_open carries its own workspace)
+        const size_t need = open_f64_workspace_bytes(ny, nx);
+        void* scratch = nullptr;
+        SMRF_CUDA(cudaMallocAsync(&scratch, need, st));
+        int rc = open_f64_rank((const double*)in, ny, nx, pitch, scratch, need, mask, when_dropped, &window, &threshold, 1,
+                               window_index, 0, row_lo, row_hi, (double*)out, pitch, st);
+        cudaFreeAsync(scratch, st);
+        return rc;
+    }
     if (open_march_available(dtype, window, negate) && !open_force_generic())
-        return open_window_march(in, out, mask, when_dropped, ny, nx, pitch, dtype, window, threshold, window_index,
+        return open_window_march(in, out, tmp, mask, when_dropped, ny, nx, pitch, dtype, window, threshold, window_index,
                                  negate, row_lo, row_hi, st);
     return open_window_generic(in, out, tmp, mask, when_dropped, ny, nx, pitch, dtype, window, threshold,
                                window_index, negate, row_lo, row_hi, st);
@@ -164,8 +198,11 @@ int smrf_progressive_open(const void* surface, void* workspace, size_t workspace
     }
     if (n_windows == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_rank_space(dtype, windows_host, n_windows, negate))
+        return open_f64_rank((const double*)surface, ny, nx, nx, workspace, workspace_bytes, mask, when_dropped, windows_host,
+                             thresholds_host, n_windows, 0, n_windows > 1, 0, ny, (double*)last_out, nx, st);
     const size_t es = dtype == SMRF_F64 ? 8 : 4;
-    const size_t plane = need / 3;
+    const size_t plane = (((size_t)ny * (size_t)aligned_pitch(nx, dtype) * es + 255) & ~(size_t)255);
     // The windows ping-pong between two workspace surfaces whose rows are padded to 16 bytes, so the
     // marching kernels take their vector paths whatever nx is; the caller's surface is never written.
     const int64_t pitch = aligned_pitch(nx, dtype);

@@ -118,3 +118,25 @@ def test_smrf_is_invariant_under_point_order(env):
     assert int((oc1 != oc2).sum()) == 0
     assert float((Z1 - Z2).abs().max()) <= 1e-4
     assert int((op1[perm] != op2).sum()) <= 20
+
+
+@pytest.mark.parametrize('w', [1, 4, 18])
+def test_opening_2048_against_the_oracle(w):
+    """One full-width grid against the oracle itself (not a property): 2048 x 2048 cells, five column strips and
+    several row segments of the marching kernel."""
+    import torch
+    from neilpy_b200 import _lib
+    from neilpy_b200.api import _ptr, _stream, _code
+    from neilpy_b200.synth import synth_dem
+    from oracle import smrf_oracle as O
+    lib = _lib.load()
+    Z = synth_dem(2048, 2048, seed=3, nan_frac=0.0).astype(np.float32)
+    Z += np.random.default_rng(1).normal(0, 0.2, Z.shape).astype(np.float32)
+    ref = O.opening(Z.astype(np.float64), O.disk(w))
+    zin = torch.as_tensor(Z).cuda()
+    out, tmp = torch.empty_like(zin), torch.empty_like(zin)
+    mask = torch.zeros(zin.shape, dtype=torch.uint8, device='cuda')
+    _lib.check(lib.smrf_open_window(_ptr(zin), _ptr(out), _ptr(tmp), _ptr(mask), None, 2048, 2048, 2048, _code(zin.dtype), w,
+                                    0.15 * w, 0, 0, 0, 2048, _stream()), 'smrf_open_window')
+    assert np.array_equal(out.cpu().numpy().astype(np.float64), ref)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), (Z.astype(np.float64) - ref) > 0.15 * w)

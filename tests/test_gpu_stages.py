@@ -116,7 +116,7 @@ def open_window(nb, Z, w, thr=0.0, negate=0, rows=None):
 
 
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])
-@pytest.mark.parametrize('w', [1, 2, 3, 4, 5, 6, 7, 8, 11, 13, 16, 17, 18, 19, 20, 21, 25, 33, 36, 40, 41])
+@pytest.mark.parametrize('w', [1, 2, 3, 4, 5, 6, 7, 8, 11, 13, 16, 17, 18, 19, 20, 21, 25, 33, 36, 40, 41, 44, 48, 56, 64, 72])
 def test_single_opening_bit_exact(nb, dtype, w):
     # 1000 columns: two column strips of the marching kernel; 300 rows: several row segments
     Z = surface(300, 1000, w, dtype)
@@ -151,6 +151,33 @@ def test_march_and_direct_kernels_agree(nb, monkeypatch):
     for w, (s, m) in a.items():
         s2, m2 = open_window(nb, Z, w, thr=0.1 * w)
         assert np.array_equal(s, s2) and np.array_equal(m, m2)
+
+
+def test_tma_and_cp_async_loaders_agree(nb, monkeypatch):
+    """rows that the TMA unit can describe (16-byte aligned) take the TMA loader; SMRF_OPEN_NO_TMA=1 forces
+    the cp.async loader of the same kernel.  Identical results, including at every image border."""
+    Z = surface(211, 1500, 5, np.float32)
+    a = {w: open_window(nb, Z, w, thr=0.1 * w) for w in (1, 2, 4, 9, 18, 30, 47, 72)}
+    monkeypatch.setenv('SMRF_OPEN_NO_TMA', '1')
+    for w, (s, m) in a.items():
+        s2, m2 = open_window(nb, Z, w, thr=0.1 * w)
+        assert np.array_equal(s, s2) and np.array_equal(m, m2), w
+
+
+def test_float64_rank_space_equals_the_direct_kernels(nb, monkeypatch):
+    """float64 surfaces are opened in rank space (csrc/rank.cu): bit-identical to the brute-force float64
+    kernels, with ties, negative values, signed zeros and NaN cells in the surface."""
+    Z = surface(190, 700, 21, np.float64)
+    Z[40:60, 100:160] = Z[40, 100]            # ties
+    Z[100:110, 300:320] *= -1.0
+    Z[5, 7] = 0.0
+    Z[5, 8] = -0.0
+    Z[150, 650] = np.nan
+    windows = np.array([1, 2, 3, 5, 9, 18])
+    m1, w1 = nb.progressive_filter(Z, windows, 1, .15, return_when_dropped=True)
+    monkeypatch.setenv('SMRF_OPEN_IMPL', 'generic')
+    m2, w2 = nb.progressive_filter(Z, windows, 1, .15, return_when_dropped=True)
+    assert np.array_equal(m1, m2) and np.array_equal(w1, w2)
 
 
 def test_open_window_row_band(nb):
