@@ -93,6 +93,35 @@ int smrf_bin_finalize_partial(void* grid, int64_t ny, int64_t nx, int dtype, int
 int smrf_bin_mark_empty(void* grid, uint8_t* empty, int64_t ny, int64_t nx, int dtype, int bin_type,
                         void* stream);
 
+/* ---- row-band sharding: every point travels once to the rank that owns its row band.
+ * With the points of a band resident on its rank, binning (neilpy.py:1142-1161) and interpolation +
+ * classification (neilpy.py:1772-1795) are band-local.  The owner of a point is the band of floor(row), the
+ * row computed with the binning's own arithmetic, bands being `rows_per_band` rows each.
+ *   smrf_route_plan   : dest[i] = owner band (world = not in the grid / non-finite), counts[0..world] += 1
+ *                       (device int64[world + 1], zeroed here)
+ *   smrf_route_pack   : writes the points grouped by destination into the send buffer -- one float4 stream
+ *                       (out_xyzw; float32 inputs) or three float64 columns -- and perm[i] = slot of point i;
+ *                       cursors[d] (device int64[world + 1]) must hold the first slot of every destination
+ *                       and is advanced
+ *   smrf_route_unpack : out[i] = back[perm[i]] (the classification that came back, in the caller's order)
+ *   smrf_bin_accumulate_band / smrf_classify_band : the band forms of smrf_bin_accumulate / smrf_classify:
+ *                       `band` / `coef_band` hold rows [row0, row0 + rows) of the ny x nx grid; a point of
+ *                       another band counts as out of range (binning) / must not occur (classify: the 4 x 4
+ *                       taps of a point in cell row r span rows r-2 .. r+2 of the interleaved coefficients). */
+int smrf_route_plan(const void* x, const void* y, int64_t n, int point_fmt, const double* inv6_host, int64_t ny,
+                    int64_t nx, int64_t rows_per_band, int world, uint8_t* dest, int64_t* counts, void* stream);
+int smrf_route_pack(const void* x, const void* y, const void* z, int64_t n, int point_fmt, int world,
+                    const uint8_t* dest, int64_t* cursors, void* out_xyzw, double* out_x, double* out_y,
+                    double* out_z, int64_t* perm, void* stream);
+int smrf_route_unpack(const uint8_t* back, const int64_t* perm, int64_t n, uint8_t* out, void* stream);
+int smrf_bin_accumulate_band(const void* x, const void* y, const void* z, int64_t n, int point_fmt,
+                             const double* inv6_host, void* band, int64_t ny, int64_t nx, int64_t row0,
+                             int64_t rows, int dtype, int bin_type, int64_t* out_of_range, void* stream);
+int smrf_classify_band(const void* x, const void* y, const void* z, int64_t n, int point_fmt,
+                       const double* inv6_host, const void* coef_band, int64_t ny, int64_t nx, int64_t row0,
+                       int64_t rows, int dtype, double elevation_threshold, double elevation_scaler,
+                       uint8_t* is_object, void* stream);
+
 /* ---- inpaint_nans_by_springs --------------------------------- neilpy.py:1227-1271
  * Discrete harmonic fill of the NaN cells of `grid` (in place): for every NaN cell
  * deg*u - sum(NaN nbrs u) = sum(known nbrs a), deg = number of in-grid 4-neighbours

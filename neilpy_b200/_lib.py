@@ -32,6 +32,11 @@ SIGNATURES = {
     'smrf_bin_finalize': (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     'smrf_bin_finalize_partial': (_i32, [_vp, _i64, _i64, _i32, _i32, _vp]),
     'smrf_bin_mark_empty': (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp]),
+    'smrf_route_plan': (_i32, [_vp, _vp, _i64, _i32, _dp, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
+    'smrf_route_pack': (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'smrf_route_unpack': (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    'smrf_bin_accumulate_band': (_i32, [_vp, _vp, _vp, _i64, _i32, _dp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp]),
+    'smrf_classify_band': (_i32, [_vp, _vp, _vp, _i64, _i32, _dp, _vp, _i64, _i64, _i64, _i64, _i32, _dbl, _dbl, _vp, _vp]),
     'smrf_inpaint_workspace_bytes': (_sz, [_i64, _i64]),
     'smrf_inpaint_layout': (_i32, [_i64, _i64, C.POINTER(C.c_int64)]),
     'smrf_inpaint_setup': (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _i32, _i32, _vp]),

@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(256) bin_init_kernel(typename KeyOf<T>::type* 
 template <typename T, int FMT>
 __global__ void __launch_bounds__(256) bin_accumulate_kernel(PointLoader<FMT> pts, int64_t n, Inv6 inv,
                                                              typename KeyOf<T>::type* keys, int64_t ny, int64_t nx,
-                                                             int bin_type, int64_t* out_of_range) {
+                                                             int bin_type, int64_t* out_of_range, int64_t row0,
+                                                             int64_t rows) {
     int bad = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double x, y, z;
@@ -104,8 +105,12 @@ __global__ void __launch_bounds__(256) bin_accumulate_kernel(PointLoader<FMT> pt
         r = floor(r);
         // NaN compares false -> counted as out of range, as np.ravel_multi_index would raise
         if (!(c >= 0.0 && c < (double)nx && r >= 0.0 && r < (double)ny)) { ++bad; continue; }
+        // `keys` holds rows [row0, row0 + rows) of the grid (the whole grid unless row-band sharded); a point
+        // routed to the wrong band is reported like an out-of-range one
+        const int64_t rl = (int64_t)r - row0;
+        if (rl < 0 || rl >= rows) { ++bad; continue; }
         if (z != z) continue;  // pandas groupby().min()/max() skips NaN
-        int64_t cell = (int64_t)r * nx + (int64_t)c;
+        int64_t cell = rl * nx + (int64_t)c;
         typename KeyOf<T>::type k = KeyOf<T>::key((T)z);
         if (bin_type == SMRF_BIN_MIN) atomicMin(&keys[cell], k);
         else atomicMax(&keys[cell], k);
@@ -179,18 +184,19 @@ using namespace smrf;
 
 template <typename T>
 static int bin_accumulate_t(const void* x, const void* y, const void* z, int64_t n, int point_fmt, Inv6 inv,
-                            void* grid, int64_t ny, int64_t nx, int bin_type, int64_t* oor, cudaStream_t st) {
+                            void* grid, int64_t ny, int64_t nx, int bin_type, int64_t* oor, cudaStream_t st,
+                            int64_t row0, int64_t rows) {
     using K = typename KeyOf<T>::type;
     int g = grid_for(n, 256, 16);
     switch (point_fmt) {
         case SMRF_PTS_SOA_F64:
-            bin_accumulate_kernel<T, SMRF_PTS_SOA_F64><<<g, 256, 0, st>>>(make_loader<SMRF_PTS_SOA_F64>(x, y, z), n, inv, (K*)grid, ny, nx, bin_type, oor);
+            bin_accumulate_kernel<T, SMRF_PTS_SOA_F64><<<g, 256, 0, st>>>(make_loader<SMRF_PTS_SOA_F64>(x, y, z), n, inv, (K*)grid, ny, nx, bin_type, oor, row0, rows);
             break;
         case SMRF_PTS_XYZW_F32:
-            bin_accumulate_kernel<T, SMRF_PTS_XYZW_F32><<<g, 256, 0, st>>>(make_loader<SMRF_PTS_XYZW_F32>(x, y, z), n, inv, (K*)grid, ny, nx, bin_type, oor);
+            bin_accumulate_kernel<T, SMRF_PTS_XYZW_F32><<<g, 256, 0, st>>>(make_loader<SMRF_PTS_XYZW_F32>(x, y, z), n, inv, (K*)grid, ny, nx, bin_type, oor, row0, rows);
             break;
         case SMRF_PTS_SOA_F32:
-            bin_accumulate_kernel<T, SMRF_PTS_SOA_F32><<<g, 256, 0, st>>>(make_loader<SMRF_PTS_SOA_F32>(x, y, z), n, inv, (K*)grid, ny, nx, bin_type, oor);
+            bin_accumulate_kernel<T, SMRF_PTS_SOA_F32><<<g, 256, 0, st>>>(make_loader<SMRF_PTS_SOA_F32>(x, y, z), n, inv, (K*)grid, ny, nx, bin_type, oor, row0, rows);
             break;
         default:
             set_error("smrf_bin_accumulate: bad point_fmt");
@@ -262,8 +268,23 @@ int smrf_bin_accumulate(const void* x, const void* y, const void* z, int64_t n, 
     if (n == 0) return 0;
     Inv6 inv{inv6_host[0], inv6_host[1], inv6_host[2], inv6_host[3], inv6_host[4], inv6_host[5]};
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == SMRF_F32) return bin_accumulate_t<float>(x, y, z, n, point_fmt, inv, grid, ny, nx, bin_type, out_of_range, st);
-    if (dtype == SMRF_F64) return bin_accumulate_t<double>(x, y, z, n, point_fmt, inv, grid, ny, nx, bin_type, out_of_range, st);
+    if (dtype == SMRF_F32) return bin_accumulate_t<float>(x, y, z, n, point_fmt, inv, grid, ny, nx, bin_type, out_of_range, st, 0, ny);
+    if (dtype == SMRF_F64) return bin_accumulate_t<double>(x, y, z, n, point_fmt, inv, grid, ny, nx, bin_type, out_of_range, st, 0, ny);
+    SMRF_CHECK_ARG(false, "bad dtype");
+}
+
+int smrf_bin_accumulate_band(const void* x, const void* y, const void* z, int64_t n, int point_fmt,
+                             const double* inv6_host, void* band, int64_t ny, int64_t nx, int64_t row0, int64_t rows,
+                             int dtype, int bin_type, int64_t* out_of_range, void* stream) {
+    SMRF_CHECK_ARG(inv6_host && band && out_of_range, "null pointer");
+    SMRF_CHECK_ARG(ny > 0 && nx > 0 && n >= 0 && row0 >= 0 && rows > 0 && row0 + rows <= ny, "bad size / row band");
+    SMRF_CHECK_ARG(bin_type == SMRF_BIN_MIN || bin_type == SMRF_BIN_MAX, "This type not supported.");
+    if (n == 0) return 0;
+    SMRF_CHECK_ARG(x && (point_fmt == SMRF_PTS_XYZW_F32 || (y && z)), "null points");
+    Inv6 inv{inv6_host[0], inv6_host[1], inv6_host[2], inv6_host[3], inv6_host[4], inv6_host[5]};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SMRF_F32) return bin_accumulate_t<float>(x, y, z, n, point_fmt, inv, band, ny, nx, bin_type, out_of_range, st, row0, rows);
+    if (dtype == SMRF_F64) return bin_accumulate_t<double>(x, y, z, n, point_fmt, inv, band, ny, nx, bin_type, out_of_range, st, row0, rows);
     SMRF_CHECK_ARG(false, "bad dtype");
 }
 

@@ -221,6 +221,11 @@ static void classify_launch(const void* x, const void* y, const void* z, int64_t
                                                slope, drop, when_pt);
 }
 
+static int classify_any(const void* x, const void* y, const void* z, int64_t n, int point_fmt, const double* inv6_host,
+                        const void* coef_z, const void* coef_s, int64_t ny, int64_t nx, int dtype,
+                        double elevation_threshold, double elevation_scaler, uint8_t* is_object, double* elevation,
+                        double* slope_out, const uint8_t* drop_raster, uint8_t* when_dropped_pt, void* stream);
+
 extern "C" {
 
 size_t smrf_spline_workspace_bytes(int64_t ny, int64_t nx) {
@@ -269,7 +274,36 @@ int smrf_classify(const void* x, const void* y, const void* z, int64_t n, int po
     SMRF_CHECK_ARG(ny >= 4 && nx >= 4 && ny < (1LL << 30) && nx < (1LL << 30), "bad grid size");
     SMRF_CHECK_ARG(dtype == SMRF_F32 || dtype == SMRF_F64, "bad dtype");
     SMRF_CHECK_ARG(!when_dropped_pt || drop_raster, "when_dropped_pt needs drop_raster");
+    return classify_any(x, y, z, n, point_fmt, inv6_host, coef_z, coef_s, ny, nx, dtype, elevation_threshold, elevation_scaler,
+                        is_object, elevation, slope_out, drop_raster, when_dropped_pt, stream);
+}
+
+/* Row-band sharding: `coef_band` holds rows [row0, row0 + rows) of the interleaved (z, slope) coefficient grid; every
+ * point must be interpolated from those rows only (points of the band's own rows need two rows of margin on each
+ * side: the 4 x 4 taps of a point in cell row r span rows r-2 .. r+2). */
+int smrf_classify_band(const void* x, const void* y, const void* z, int64_t n, int point_fmt, const double* inv6_host,
+                       const void* coef_band, int64_t ny, int64_t nx, int64_t row0, int64_t rows, int dtype,
+                       double elevation_threshold, double elevation_scaler, uint8_t* is_object, void* stream) {
+    SMRF_CHECK_ARG(inv6_host && coef_band, "null pointer");
+    SMRF_CHECK_ARG(row0 >= 0 && rows > 0 && row0 + rows <= ny, "bad row band");
+    SMRF_CHECK_ARG(dtype == SMRF_F32 || dtype == SMRF_F64, "bad dtype");
+    // the kernel addresses coefficients by global row: hand it the address row 0 would have
+    const size_t es = dtype == SMRF_F32 ? 4 : 8;
+    const char* virt = (const char*)coef_band - (size_t)row0 * (size_t)nx * 2 * es;
+    return classify_any(x, y, z, n, point_fmt, inv6_host, virt, nullptr, ny, nx, dtype, elevation_threshold, elevation_scaler,
+                        is_object, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+}  // extern "C"
+
+static int classify_any(const void* x, const void* y, const void* z, int64_t n, int point_fmt, const double* inv6_host,
+                        const void* coef_z, const void* coef_s, int64_t ny, int64_t nx, int dtype,
+                        double elevation_threshold, double elevation_scaler, uint8_t* is_object, double* elevation,
+                        double* slope_out, const uint8_t* drop_raster, uint8_t* when_dropped_pt, void* stream) {
     if (n <= 0) return 0;
+    SMRF_CHECK_ARG(x && is_object, "null pointer");
+    SMRF_CHECK_ARG(point_fmt == SMRF_PTS_XYZW_F32 || (y && z), "y/z null");
+    SMRF_CHECK_ARG(ny >= 4 && nx >= 4 && ny < (1LL << 30) && nx < (1LL << 30), "bad grid size");
     Inv6 inv{inv6_host[0], inv6_host[1], inv6_host[2], inv6_host[3], inv6_host[4], inv6_host[5]};
     cudaStream_t st = (cudaStream_t)stream;
 #define SMRF_GO(T, F)                                                                                         \
@@ -291,5 +325,3 @@ int smrf_classify(const void* x, const void* y, const void* z, int64_t n, int po
     count_launches(1);
     return 0;
 }
-
-}  // extern "C"

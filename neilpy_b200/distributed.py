@@ -6,8 +6,8 @@ rank, and every stage exchanges exactly the rows it depends on, so the result is
 the single-GPU path (and the reference) produces for the whole cloud:
 
   extent        all-reduce(min/max) of 4 doubles
-  binning       each rank bins its points into a full-grid replica (+inf in untouched
-                cells), then reduce-scatter(MIN) by row band
+  binning       every point travels once to the rank that owns its row band (all-to-all of the
+                point records, csrc/route.cu); binning is then band-local
   inpaint       conjugate gradients over all bands (all-reduce of the two dot products and
                 one boundary row of the search direction per iteration); each band is
                 preconditioned by its own multigrid V-cycle (block Jacobi over bands)
@@ -16,7 +16,8 @@ the single-GPU path (and the reference) produces for the whole cloud:
   slope         1 halo row
   spline        the row-direction solve is local; the column-direction recurrences contract
                 by 0.268 per row, so 80 halo rows reproduce the global solve to rounding
-  classify      all-gather of the two coefficient grids; each rank classifies its own points
+  classify      band-local on the routed points (a band keeps 4 coefficient rows of each neighbour);
+                one byte per point travels back and is put in the caller's order
 
 The halo / partition helpers are backend-agnostic (they are exercised with gloo on CPU
 tensors in tests/test_distributed_cpu.py); the compute calls need the CUDA library.
@@ -32,6 +33,7 @@ import torch
 from .comm import as_comm
 
 SPLINE_HALO = 80
+COEF_MARGIN = 4        # coefficient rows of the neighbouring bands a band keeps for the taps of its own points
 
 
 # ------------------------------------------------------------------ partition + halo helpers
@@ -302,6 +304,72 @@ def _open_windows_band(lib, band, windows, thresholds, mask, when, negate, group
     return last
 
 
+class _Routed:
+    """This rank's share of the cloud after the all-to-all: the points of its own row band (device, in one of the
+    library's stream layouts), and what is needed to send one byte per point back to where it came from."""
+
+    def __init__(self):
+        self.n, self.fmt, self.ptrs, self.keep = 0, None, (None, None, None), None
+        self.out_of_grid = 0
+
+
+def _route_points(lib, pts, inv6, ny, nx, per, comm, dev):
+    """smrf_route_plan / _pack + all-to-all (see csrc/route.cu).  With one rank nothing moves."""
+    _lib, api = _api()
+    world, rank = comm.world, comm.rank
+    R = _Routed()
+    if world == 1:
+        R.n, R.fmt, R.ptrs, R.keep = pts.n, pts.fmt, pts.ptrs, pts
+        R.send_back = lambda cls: cls
+        return R
+    st = api._stream
+    n = pts.n
+    dest = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    counts = torch.zeros(world + 1, dtype=torch.int64, device=dev)
+    _lib.check(lib.smrf_route_plan(pts.ptrs[0], pts.ptrs[1], n, pts.fmt, inv6, ny, nx, per, world, api._ptr(dest),
+                                   api._ptr(counts), st()), 'smrf_route_plan')
+    allc = torch.empty(world * world, dtype=torch.int64, device=dev)
+    comm.all_gather(allc, counts[:world].contiguous())
+    host = torch.cat([counts, allc]).cpu()
+    send = [int(v) for v in host[:world]]
+    R.out_of_grid = int(host[world])
+    recv = [int(host[world + 1 + src * world + rank]) for src in range(world)]
+    n_send, n_recv = sum(send), sum(recv)
+    cursors = torch.tensor([sum(send[:d]) for d in range(world)] + [n_send], dtype=torch.int64, device=dev)
+    perm = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    f32 = pts.fmt != _lib.PTS_SOA_F64
+    if f32:
+        sbuf = [torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)]
+        args = (api._ptr(sbuf[0]), None, None, None)
+    else:
+        sbuf = [torch.empty(max(n, 1), dtype=torch.float64, device=dev) for _ in range(3)]
+        args = (None, api._ptr(sbuf[0]), api._ptr(sbuf[1]), api._ptr(sbuf[2]))
+    if n:
+        _lib.check(lib.smrf_route_pack(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], n, pts.fmt, world, api._ptr(dest),
+                                       api._ptr(cursors), args[0], args[1], args[2], args[3], api._ptr(perm), st()),
+                   'smrf_route_pack')
+    rbuf = []
+    for sb in sbuf:                                   # points not in the grid (dest == world) sit behind n_send: never sent
+        rb = torch.empty((n_recv,) + tuple(sb.shape[1:]), dtype=sb.dtype, device=dev)
+        comm.all_to_all(rb, sb[:n_send], recv, send)
+        rbuf.append(rb)
+    R.n, R.keep = n_recv, rbuf
+    if f32:
+        R.fmt, R.ptrs = _lib.PTS_XYZW_F32, (api._ptr(rbuf[0]), C.c_void_p(0), C.c_void_p(0))
+    else:
+        R.fmt, R.ptrs = _lib.PTS_SOA_F64, tuple(api._ptr(t) for t in rbuf)
+
+    def send_back(cls):
+        back = torch.zeros(max(n, 1), dtype=torch.uint8, device=dev)
+        comm.all_to_all(back[:n_send], cls, send, recv)
+        out = torch.empty(n, dtype=torch.uint8, device=dev)
+        if n:
+            _lib.check(lib.smrf_route_unpack(api._ptr(back), api._ptr(perm), n, api._ptr(out), st()), 'smrf_route_unpack')
+        return out
+    R.send_back = send_back
+    return R
+
+
 def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_threshold=.5, elevation_scaler=1.25,
                  low_filter_slope=5, dtype=None, inpaint_tol=None, group=None, gather=False, comm=None):
     """`neilpy.smrf` (neilpy.py:1685-1808) over all ranks of `group`.
@@ -365,28 +433,21 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     r0, r1 = band_bounds(ny, world, rank)
     rows = r1 - r0
 
-    # ---- binning: full-grid replica per rank, reduce-scatter(MIN) to bands
-    replica = torch.empty((per * world, nx), dtype=tdtype, device=dev)
+    # ---- every point travels once to the rank that owns its row band (all-to-all); binning is band-local
+    routed = _route_points(lib, pts, inv6, ny, nx, per, comm, dev)
+    Zmin = torch.empty((rows, nx), dtype=tdtype, device=dev)
+    empty = torch.empty((rows, nx), dtype=torch.uint8, device=dev)
     oor = torch.zeros(1, dtype=torch.int64, device=dev)
-    _lib.check(lib.smrf_bin_init(api._ptr(replica), per * world, nx, code, _lib.BIN_MIN, st()), 'smrf_bin_init')
-    if pts.n:
-        _lib.check(lib.smrf_bin_accumulate(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, api._ptr(replica),
-                                           ny, nx, code, _lib.BIN_MIN, api._ptr(oor), st()), 'smrf_bin_accumulate')
+    _lib.check(lib.smrf_bin_init(api._ptr(Zmin), rows, nx, code, _lib.BIN_MIN, st()), 'smrf_bin_init')
+    if routed.n:
+        _lib.check(lib.smrf_bin_accumulate_band(routed.ptrs[0], routed.ptrs[1], routed.ptrs[2], routed.n, routed.fmt, inv6,
+                                                api._ptr(Zmin), ny, nx, r0, rows, code, _lib.BIN_MIN, api._ptr(oor), st()),
+                   'smrf_bin_accumulate_band')
+    oor += routed.out_of_grid
     comm.all_reduce(oor)
     if int(oor.item()):                                  # api._bin raises the same (np.ravel_multi_index's message)
         raise ValueError('invalid entry in coordinates array')
-    _lib.check(lib.smrf_bin_finalize_partial(api._ptr(replica), per * world, nx, code, _lib.BIN_MIN, st()),
-               'smrf_bin_finalize_partial')
-    padded = torch.empty((per, nx), dtype=tdtype, device=dev)
-    if world > 1:
-        comm.reduce_scatter(padded, replica, 'min')
-    else:
-        padded.copy_(replica)
-    del replica
-    Zmin = padded[:rows]
-    empty = torch.empty((rows, nx), dtype=torch.uint8, device=dev)
-    _lib.check(lib.smrf_bin_mark_empty(api._ptr(Zmin), api._ptr(empty), rows, nx, code, _lib.BIN_MIN, st()),
-               'smrf_bin_mark_empty')
+    _lib.check(lib.smrf_bin_finalize(api._ptr(Zmin), api._ptr(empty), rows, nx, code, _lib.BIN_MIN, st()), 'smrf_bin_finalize')
     mark('binning')
 
     # ---- inpaint, low outliers, progressive filter, punch, inpaint
@@ -418,8 +479,11 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     colf = api._factors(nx, dev)
     rowf_all = api._factors(ny, dev).view(5, ny)
 
-    # interleaved (DTM, slope) coefficient pairs of this band, then one all-gather
-    mine = torch.zeros((per, nx, 2), dtype=tdtype, device=dev)
+    # interleaved (DTM, slope) coefficient pairs of this band plus COEF_MARGIN rows of its neighbours': the 4 x 4 taps of
+    # a point of this band never reach further, so the routed points are classified here and no coefficient leaves the band
+    top_m = min(COEF_MARGIN, r0)
+    bot_m = min(COEF_MARGIN, ny - r1)
+    coef = torch.empty((top_m + rows + bot_m, nx, 2), dtype=tdtype, device=dev)
     for k, band in enumerate((Zpro, S)):
         b, tp = with_halo(band, SPLINE_HALO, group)
         g0 = r0 - tp
@@ -428,20 +492,15 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
         c = torch.empty_like(b)
         _lib.check(lib.smrf_spline_prefilter(api._ptr(b), api._ptr(c), 1, 0, b.shape[0], nx, code, api._ptr(rf),
                                              api._ptr(colf), api._ptr(wsp), wsp.numel(), st()), 'smrf_spline_prefilter')
-        mine[:rows, :, k] = c[tp:tp + rows]
+        coef[:, :, k] = c[tp - top_m:tp + rows + bot_m]
         del wsp, c, b
-    full = torch.empty((per * world, nx, 2), dtype=tdtype, device=dev)
-    if world > 1:
-        comm.all_gather(full, mine)
-    else:
-        full.copy_(mine)
-    coef = full[:ny]
     mark('slope+spline')
-    is_obj = torch.empty(pts.n, dtype=torch.uint8, device=dev)
-    if pts.n:
-        _lib.check(lib.smrf_classify(pts.ptrs[0], pts.ptrs[1], pts.ptrs[2], pts.n, pts.fmt, inv6, api._ptr(coef),
-                                     None, ny, nx, code, float(elevation_threshold), float(elevation_scaler),
-                                     api._ptr(is_obj), None, None, None, None, st()), 'smrf_classify')
+    cls = torch.empty(routed.n, dtype=torch.uint8, device=dev)
+    if routed.n:
+        _lib.check(lib.smrf_classify_band(routed.ptrs[0], routed.ptrs[1], routed.ptrs[2], routed.n, routed.fmt, inv6,
+                                          api._ptr(coef), ny, nx, r0 - top_m, coef.shape[0], code, float(elevation_threshold),
+                                          float(elevation_scaler), api._ptr(cls), st()), 'smrf_classify_band')
+    is_obj = routed.send_back(cls)                        # the answers travel back and are put in the caller's order
     mark('classify')
     res = {'t': t, 'shape': (ny, nx), 'rows': (r0, r1), 'is_object_point': is_obj.view(torch.bool),
            'info': {'inpaint1': info1, 'inpaint2': info2, 'timing_ms': timing}}
