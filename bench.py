@@ -236,13 +236,20 @@ def opening_roofline(torch, nb, Zsurf, reps, peaks):
         g = json.load(open(tp))['grids'].get('%dx%d' % (ny, nx))
         if g:
             traffic = g['mean_bytes_per_launch']
-    roof = {'bound': 'hbm', 'kernel': 'open_march_kernel<W> (18 launches, W=1..18)', 'achieved': achieved,
+    roof = {'bound': 'hbm', 'kernel': 'progressive opening W=1..18: open_march_kernel<W> (fused, W <= 6) and open_pass_kernel<W> x 2 (erosion + dilation, W >= 7); one CUDA-event interval per window', 'achieved': achieved,
             'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peaks['source'], 'traffic': traffic,
-            'traffic_source': 'profiles/r1_opening_traffic.json (ncu dram__bytes_read+write, mean over the 18 launches)' if traffic else None,
+            'traffic_source': 'STATIC: committed ncu capture profiles/r1_opening_traffic.json (dram__bytes_read+write, mean over the 18 launches of round 1; the round-2 two-pass kernels add the intermediate plane, see profiles/README.md)' if traffic else None,
             'algorithmic_bytes_per_launch': bytes_per_launch, 'avg_launch_ms': total_ms / 18,
             'per_window_ms': [round(float(v), 4) for v in per_w],
             'per_window_frac': [round(float(bytes_per_launch / (v * 1e-3) / 1e9 / peak), 4) for v in per_w],
             'frac_of_nominal_8TBs': achieved / 8000.0}
+    ops = [4 * int(w) + 1 for w in windows]      # 3-input min/max instructions per cell: growth w + fold (2w+1)/2, two passes
+    roof['alu'] = {'what': 'FMNMX3 (3-input min/max) thread-instructions; peak = 64 lanes/clk/SM x 148 SMs x 1965 MHz, measured '
+                           'by tools/fmnmx_bench.cu (profiles/r2_fmnmx_microbench.log)',
+                   'fmnmx3_per_cell': float(sum(ops)), 'peak_per_s': FMNMX3_PEAK,
+                   'achieved_frac': cells * float(sum(ops)) / (total_ms * 1e-3) / FMNMX3_PEAK,
+                   'per_window_frac': [round(float(cells * o / (v * 1e-3) / FMNMX3_PEAK), 4) for o, v in zip(ops, per_w)],
+                   'hbm_frac_if_alu_bound': float(10.0 * 18 / sum(ops) * FMNMX3_PEAK / 1e9 / peak)}
     extra = {'opening_mcells_per_s': cells / (total_ms * 1e-3) / 1e6, 'opening_grid': [ny, nx],
              'opening_cell_windows_per_s': 18 * cells / (total_ms * 1e-3),
              'opening_variant': lib.smrf_open_variant(code, 18).decode()}
@@ -362,19 +369,59 @@ def run_gpu(args):
 
     parity = parity_block(torch, nb, dev, rank, world, args.parity_points)
 
+    # ---- per-stage clock of the sharded path (one extra, untimed step: the clock synchronises after every stage)
+    stage_ms = None
+    if world > 1:
+        os.environ['SMRF_TIMING'] = '1'
+        stage_ms = smrf_sharded(pts, **PARAMS)['info']['timing_ms']
+        os.environ.pop('SMRF_TIMING', None)
+
+    # ---- the float64 arm (the reference's own dtype: float64 x, y, z -> float64 grids; the opening runs in rank space)
+    f64 = None
+    if world == 1 and args.f64_points > 0:
+        f64 = f64_leg(torch, nb, dev, args.f64_points)
+
+    # ---- BASELINE.json configs[3] and configs[4] (sized for 8 GPUs; any N runs them when asked to)
+    band0 = Z.contiguous() if world > 1 else None
+    Zfull = Z
+    del Z, oc, op
+    c4 = c5 = None
+    c4_points = args.c4_points if args.c4_points >= 0 else (125_000_000 if world == 8 else 0)
+    c5_rows = args.c5_rows if args.c5_rows >= 0 else (16384 if world == 8 else 0)
+    if c4_points > 0 or c5_rows > 0:
+        del pts
+        torch.cuda.empty_cache()
+        pts = None
+    if c4_points > 0:
+        try:
+            c4 = config4_leg(torch, dev, rank, world, c4_points)
+        except Exception as e:                           # noqa: BLE001  (report, do not hide the main line)
+            c4 = {'error': repr(e)}
+    if c5_rows > 0:
+        try:
+            c5 = config5_leg(torch, dev, rank, world, total_rows=c5_rows)
+        except Exception as e:                           # noqa: BLE001
+            c5 = {'error': repr(e)}
+
     line = None
     if rank == 0:
         # ---- roofline of the opening kernels on this workload's grid, and the C3 opening-only figure
         peaks = load_peaks()
+        if pts is None:
+            pts = host.to(dev)
         if world == 1:
             stages = {}
             nb.smrf(pts, return_stages=stages, **PARAMS)
             roof, extra = opening_roofline(torch, nb, stages['Zmin_filtered'], max(2, min(args.steps, 5)), peaks)
             extra['inpaint_iterations'] = [stages['inpaint1']['iterations'], stages['inpaint2']['iterations']]
+            try:
+                extra['roofline_inpaint'] = inpaint_roofline(torch, nb, stages, peaks)
+            except Exception as e:                       # noqa: BLE001
+                extra['roofline_inpaint'] = {'error': repr(e)}
             extra['grid'] = list(stages['Zpro'].shape)
             del stages
         else:
-            roof, extra = opening_roofline(torch, nb, Z.contiguous(), 2, peaks)   # rank 0's band, no exchange
+            roof, extra = opening_roofline(torch, nb, band0, 2, peaks)   # rank 0's band, no exchange
             extra['opening_sharded'] = sharded_open
             extra['opening_mcells_per_s_single_band'] = extra.pop('opening_mcells_per_s')
             extra['opening_mcells_per_s'] = sharded_open['mcells_per_s']
@@ -390,7 +437,7 @@ def run_gpu(args):
                 extra['las_decode'] = {'error': repr(e)}
         if world == 1:
             try:
-                extra['terrain'] = terrain_leg(torch, Z)
+                extra['terrain'] = terrain_leg(torch, Zfull)
             except Exception as e:                       # noqa: BLE001
                 extra['terrain'] = {'error': repr(e)}
         cpu = cpu_baseline_leg(args.cpu_points) if (world == 1 and args.cpu_points > 0) else None
@@ -398,7 +445,7 @@ def run_gpu(args):
                 'warmup': args.warmup, 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args),
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'step_ms': step_ms, 'roofline': roof, 'cpu_baseline': cpu,
-                'parity': parity}
+                'parity': parity, 'sharded_stage_ms_rank0': stage_ms, 'f64_input': f64, 'config4': c4, 'config5': c5}
         line.update(extra)
     if world > 1:
         dist.barrier()
@@ -457,6 +504,218 @@ def parity_block(torch, nb, dev, rank, world, n):
            'sha_point_mask': [sha(op), sha(op1)], 'sha_cell_mask': [sha(res['object_cells']), sha(oc1)]}
     out['ok'] = bool(out['cell_flips'] == 0 and out['point_flips'] == 0 and out['max_abs_dZ_m'] <= 1e-4)
     return out
+
+
+INPAINT_BYTES_PER_CELL_ITER = 52 + 17 + 21 + (9 + 14) * 4.0 / 3.0   # see inpaint_roofline
+
+
+def inpaint_roofline(torch, nb, stages, peaks):
+    """The harmonic solver on the step's own two systems, CUDA events around each solve.  Algorithmic bytes per cell
+    and CG iteration (float32 grid; float64 CG vectors u, r, p, q; float32 V-cycle): update 52 (p, q, u, r in; u, r,
+    float r out), operator 17 (p, mask in; q out), direction 21 (z, p in; p out), level-0 legs 9 + 14 (right-hand
+    side, mask, iterate / coarse correction in; iterate out), coarser levels a third of the legs again."""
+    from neilpy_b200 import _lib
+    from neilpy_b200.api import _inpaint, SMRF_INPAINT_TOL
+    lib = _lib.load()
+    out = {'bytes_per_cell_iteration': INPAINT_BYTES_PER_CELL_ITER, 'solves': []}
+    tot_ms = tot_bytes = 0.0
+    for name in ('Zmin_binned', 'Zpro_punched'):
+        src = stages[name]
+        cells = src.numel()
+        g = src.clone()
+        ws = torch.empty(lib.smrf_inpaint_workspace_bytes(*src.shape), dtype=torch.uint8, device=src.device)
+        _inpaint(lib, g, ws, SMRF_INPAINT_TOL)
+        g.copy_(src)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        info = _inpaint(lib, g, ws, SMRF_INPAINT_TOL)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        by = info['iterations'] * cells * INPAINT_BYTES_PER_CELL_ITER
+        out['solves'].append({'system': name, 'unknown_fraction': info['unknown'] / cells, 'iterations': info['iterations'],
+                              'ms': ms, 'ms_per_iteration': ms / max(1, info['iterations']), 'achieved_GBs': by / (ms * 1e-3) / 1e9})
+        tot_ms += ms; tot_bytes += by
+        del g, ws
+    out.update(bound='hbm', achieved=tot_bytes / (tot_ms * 1e-3) / 1e9, peak=peaks['hbm_gbs'], unit='GB/s',
+               frac=tot_bytes / (tot_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+               note='second system solved here without the opened-surface seed smrf() gives it (a few more iterations)')
+    return out
+
+
+def f64_leg(torch, nb, dev, n):
+    """The reference's own dtype: float64 x, y, z (UTM-sized coordinates) through the same public API -> float64
+    grids: the binning, solver and spline run in float64 as they always do, the progressive opening runs in rank
+    space (csrc/rank.cu).  Reported next to the float4 headline (the default drop-in path was unmeasured)."""
+    from neilpy_b200.synth import synth_cloud
+    from neilpy_b200 import _lib
+    from neilpy_b200.api import _progressive
+    side = float(np.sqrt(n / DENSITY))
+    x, y, z, _ = synth_cloud(n, side, side, seed=21, dtype=np.float64)
+    xd, yd, zd = [torch.from_numpy(v).to(dev) for v in (x + 500000.0, y + 5400000.0, z)]
+    st = {}
+    nb.smrf(xd, yd, zd, return_stages=st, **PARAMS)                 # warm-up; keeps the stages for the opening-only figure
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        Z, t, oc, op = nb.smrf(xd, yd, zd, **PARAMS)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    surf = st['Zmin_filtered']
+    windows = np.arange(18) + 1
+    mask = torch.zeros(surf.shape, dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+    _progressive(lib, surf, windows, .15 * (windows * 1), mask, None, None)
+    torch.cuda.synchronize()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    _progressive(lib, surf, windows, .15 * (windows * 1), mask, None, None)
+    o1.record()
+    torch.cuda.synchronize()
+    oms = o0.elapsed_time(o1)
+    s32 = surf.float()
+    m32 = torch.zeros_like(mask)
+    _progressive(lib, s32, windows, .15 * (windows * 1), m32, None, None)
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    _progressive(lib, s32, windows, .15 * (windows * 1), m32, None, None)
+    p1.record()
+    torch.cuda.synchronize()
+    return {'points': n, 'grid': list(Z.shape), 'dtype': 'f64', 'ms_per_step': ms, 'points_per_s': n / (ms * 1e-3),
+            'opening_f64_ms': oms, 'opening_f64_mcells_per_s': surf.numel() / (oms * 1e-3) / 1e6,
+            'opening_f32_same_grid_ms': p0.elapsed_time(p1), 'opening_f64_over_f32': oms / p0.elapsed_time(p1),
+            'inpaint_iterations': [st['inpaint1']['iterations'], st['inpaint2']['iterations']]}
+
+
+P4 = dict(cellsize=0.5, windows=36, slope_threshold=.15, elevation_threshold=.5, elevation_scaler=1.25)
+C4_DENSITY = 1e9 / (8192.0 * 16384.0)       # BASELINE.json configs[3]: 1 B points over 8192 m x 16384 m (7.45 / m^2)
+
+
+def _maxms(torch, dist, world, ms, dev):
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def config4_leg(torch, dev, rank, world, n, steps=2):
+    """BASELINE.json configs[3] (the north-star target): n points per GPU (125 M at 8 GPUs = 1 B), cellsize 0.5,
+    windows 36, row bands with halo exchange.  Points are generated on the device, uniform over the whole job
+    area on every rank (an arbitrary slice of the cloud, not the rank's own band)."""
+    import torch.distributed as dist
+    from neilpy_b200 import _lib
+    from neilpy_b200.distributed import smrf_sharded, _open_windows_band
+    from neilpy_b200.synth_torch import cloud_on_device
+    lib = _lib.load()
+    area = world * n / C4_DENSITY
+    ex = float(np.sqrt(area / 2.0)); ey = 2.0 * ex
+    pts = cloud_on_device(torch, n, ex, ey, dev, seed=1 + rank)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    torch.cuda.reset_peak_memory_stats(dev)
+    os.environ['SMRF_TIMING'] = '1'
+    r = smrf_sharded(pts, **P4)                       # warm-up, with the per-stage clock on (it synchronises: untimed)
+    stage_ms = r['info']['timing_ms']
+    os.environ.pop('SMRF_TIMING', None)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = smrf_sharded(pts, **P4)
+    e1.record()
+    barrier()
+    ms = _maxms(torch, dist, world, e0.elapsed_time(e1) / steps, dev)
+    peak = torch.cuda.max_memory_allocated(dev)
+    ny, nx = r['shape']
+    band = r['Zpro']
+    windows = np.arange(36) + 1
+    thr = .15 * (windows * 0.5)
+    mk = torch.zeros(band.shape, dtype=torch.uint8, device=dev)
+    _open_windows_band(lib, band, windows, thr, mk, None, 0, None)
+    barrier()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    _open_windows_band(lib, band, windows, thr, mk, None, 0, None)
+    o1.record()
+    barrier()
+    oms = _maxms(torch, dist, world, o0.elapsed_time(o1), dev)
+    # end to end with host buffers: pinned float4 in, this rank's band + point mask out as numpy
+    host = pts.cpu().pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    rh = smrf_sharded(host, **P4)
+    torch.cuda.synchronize()
+    e2e_ms = _maxms(torch, dist, world, (time.perf_counter() - t0) * 1e3, dev)
+    info = r['info']
+    out = {'workload': 'BASELINE.json configs[3]: %d points per GPU x %d GPUs (%.3g points), %.0f m x %.0f m, cellsize 0.5, '
+                       'windows 36, row bands' % (n, world, float(world) * n, ex, ey),
+           'grid': [int(ny), int(nx)], 'band_rows': int(band.shape[0]), 'ms_per_step': ms,
+           'points_per_s': world * n / (ms * 1e-3), 'steps': steps,
+           'e2e': {'ms_per_step': e2e_ms, 'points_per_s': world * n / (e2e_ms * 1e-3), 'h2d_bytes_per_step': int(host.numel() * 4),
+                   'd2h_bytes_per_step': int(rh['Zpro'].nbytes + rh['object_cells'].nbytes + rh['is_object_point'].nbytes)},
+           'opening_ms': oms, 'opening_mcells_per_s': float(ny) * nx / (oms * 1e-3) / 1e6,
+           'opening_frac_of_hbm': float(ny) * nx * 10.0 * 36 / (oms * 1e-3) / 1e9 / (world * load_peaks()['hbm_gbs']),
+           'inpaint_iterations': [info['inpaint1']['iterations'], info['inpaint2']['iterations']],
+           'object_point_fraction': float(r['is_object_point'].float().mean()),
+           'peak_memory_GB_rank0': peak / 1e9, 'stage_ms_rank0': stage_ms}
+    del pts, host, r, rh, band, mk
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
+def config5_leg(torch, dev, rank, world, total_rows=16384, nx=65536, W=72):
+    """BASELINE.json configs[4]: progressive opening only, 0.25 m cells, windows 72 (disk radii up to 72 cells),
+    a 16384 x 65536 grid in `world` row bands.  sum 2w over all windows exceeds a band, so the halo is
+    re-exchanged every few windows (neilpy_b200.distributed.plan_window_chunks)."""
+    import torch.distributed as dist
+    from neilpy_b200 import _lib
+    from neilpy_b200.distributed import _open_windows_band, band_bounds
+    from neilpy_b200.synth_torch import dem_on_device
+    lib = _lib.load()
+    r0, r1 = band_bounds(total_rows, world, rank)
+    band = dem_on_device(torch, r1 - r0, nx, dev, seed=2, row0=r0, scale=0.25)
+    windows = np.arange(W) + 1
+    thr = .15 * (windows * 0.25)
+    mk = torch.zeros(band.shape, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    _open_windows_band(lib, band, windows, thr, mk, None, 0, None)          # warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _open_windows_band(lib, band, windows, thr, mk, None, 0, None)
+    e1.record()
+    barrier()
+    ms = _maxms(torch, dist, world, e0.elapsed_time(e1), dev)
+    cells = float(total_rows) * nx
+    ops = float(sum(4 * w + 1 for w in windows))          # 3-input min/max instructions per cell: growth w + fold (2w+1)/2, two passes
+    peaks = load_peaks()
+    out = {'workload': 'BASELINE.json configs[4]: opening only, %d x %d cells at 0.25 m, windows %d, %d row bands' % (total_rows, nx, W, world),
+           'ms': ms, 'mcells_per_s': cells / (ms * 1e-3) / 1e6, 'cell_windows_per_s': cells * W / (ms * 1e-3),
+           'roofline': {'bound': 'hbm', 'achieved': cells * 10.0 * W / (ms * 1e-3) / 1e9, 'peak': world * peaks['hbm_gbs'], 'unit': 'GB/s',
+                        'frac': cells * 10.0 * W / (ms * 1e-3) / 1e9 / (world * peaks['hbm_gbs'])},
+           'alu': {'fmnmx3_per_cell': ops, 'achieved_frac_of_fmnmx_peak': cells * ops / (ms * 1e-3) / (world * FMNMX3_PEAK)},
+           'object_cell_fraction_rank0': float(mk.float().mean())}
+    del band, mk
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
+FMNMX3_PEAK = 148 * 64 * 1.965e9     # thread-instructions / s: 64 lanes / clk / SM (profiles/r2_fmnmx_microbench.log), 148 SMs, 1965 MHz
 
 
 def las_decode_leg(torch, dev, peaks, n, fmt=1):
@@ -523,6 +782,9 @@ def main():
     ap.add_argument('--cpu-points', type=int, default=600_000, help='sample size of the cpu_baseline leg (0 = skip)')
     ap.add_argument('--ref-points', type=int, default=300_000, help='points per worker cloud of --impl reference')
     ap.add_argument('--parity-points', type=int, default=4_000_000, help='sub-cloud of the sharded-vs-single parity block (0 = skip)')
+    ap.add_argument('--f64-points', type=int, default=10_000_000, help='points of the float64-input arm (0 = skip)')
+    ap.add_argument('--c4-points', type=int, default=-1, help='points per GPU of the configs[3] leg (-1: 125 M at 8 GPUs, else skip)')
+    ap.add_argument('--c5-rows', type=int, default=-1, help='total rows of the configs[4] opening-only leg (-1: 16384 at 8 GPUs, else skip)')
     ap.add_argument('--c3', type=int, default=32768, help='side of the opening-only grid (BASELINE.json configs[2]; 0 = skip)')
     args = ap.parse_args()
     args.warmup_ref = args.warmup          # the driver's W, also on the reference arm

@@ -202,8 +202,19 @@ def run_virtual_ranks(world, fn, device=None):
     return out
 
 
+class SoloComm(ThreadComm):
+    """A single rank without any process group (every collective is the identity)."""
+
+    def __init__(self):
+        self.shared, self.rank, self.world = None, 0, 1
+
+
 def as_comm(group_or_comm=None):
-    """A Comm for `None` / a torch.distributed group / an existing Comm."""
+    """A Comm for `None` / a torch.distributed group / an existing Comm.  Without an initialised process group
+    `None` is a single rank."""
     if isinstance(group_or_comm, (TorchComm, ThreadComm)):
         return group_or_comm
+    import torch.distributed as dist
+    if group_or_comm is None and not (dist.is_available() and dist.is_initialized()):
+        return SoloComm()
     return TorchComm(group_or_comm)
