@@ -186,6 +186,11 @@ int smrf_mg_setup_mask(const uint8_t* mask, int64_t ny, int64_t nx, void* worksp
 int smrf_mg_cycle_part(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, int has_above,
                        int has_below, int split, int part, void* stream);
 int smrf_mg_vcycle(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, void* stream);
+/* part 2 (the up legs of levels split-1 .. 0) with the preconditioned product formed on the way: the level-0 leg
+ * adds sum(b * z) over rows [row_lo, row_hi) of the extended band (the rows this rank owns) to *rz_slot (device
+ * double, e.g. the rz[k] slot of the band's own workspace), which replaces step phase 20. */
+int smrf_mg_cycle_up_rz(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, int has_above,
+                        int has_below, int split, double* rz_slot, int64_t row_lo, int64_t row_hi, void* stream);
 int smrf_inpaint_finish(void* grid, int64_t ny, int64_t nx, int dtype, void* workspace,
                         size_t workspace_bytes, void* stream);
 

@@ -46,6 +46,7 @@ SIGNATURES = {
     'smrf_mg_level_layout': (_i32, [_i64, _i64, _i32, C.POINTER(C.c_int64)]),
     'smrf_mg_setup_mask': (_i32, [_vp, _i64, _i64, _vp, _sz, _vp]),
     'smrf_mg_vcycle': (_i32, [_i64, _i64, _vp, _sz, _vp]),
+    'smrf_mg_cycle_up_rz': (_i32, [_i64, _i64, _vp, _sz, _i32, _i32, _i32, _vp, _i64, _i64, _vp]),
     'smrf_inpaint_finish': (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _vp]),
     'smrf_inpaint': (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _dbl, _i32, _dp, _vp]),
     'smrf_open_workspace_bytes': (_sz, [_i64, _i64, _i32, _i32]),

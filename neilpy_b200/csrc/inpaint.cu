@@ -600,9 +600,9 @@ template <bool RZ>
 __global__ void __launch_bounds__(kBlock) up_kernel(const float* __restrict__ x, const float* __restrict__ xc,
                                                     const float* __restrict__ b, const uint8_t* __restrict__ m,
                                                     float* __restrict__ xout, int64_t ny, int64_t nx, int64_t cx,
-                                                    int above, int below, Scalars* sc, int k) {
+                                                    int above, int below, double* rz_slot, int64_t rz_lo, int64_t rz_hi) {
     __shared__ TileBuf t;
-    double rz = 0.0;       // RZ (level 0, single-GPU loop): rz[k] += b . z while z is at hand -- one pass less over the fine grid
+    double rz = 0.0;       // RZ (level 0): *rz_slot += b . z over rows [rz_lo, rz_hi) while z is at hand -- one pass less over the fine grid
     const int64_t tiles_x = (nx + kTX - 1) / kTX, tiles = tiles_x * ((ny + kTY - 1) / kTY);
     for (int64_t tile = tile_first(); tile < tiles; tile += tile_step()) {
         const int64_t ty = tile / tiles_x;
@@ -622,14 +622,16 @@ __global__ void __launch_bounds__(kBlock) up_kernel(const float* __restrict__ x,
                 if (ly >= kH && ly < kTY + kH && y < ny) {
                     const float zv = jacobi(t.s0, t, ly, p.lx, kOmegaA);
                     xout[p.g0 + (int64_t)(4 * e) * nx] = zv;
-                    if constexpr (RZ) rz += (double)t.b[ly][p.lx] * (double)zv;
+                    if constexpr (RZ) {
+                        if (y >= rz_lo && y < rz_hi) rz += (double)t.b[ly][p.lx] * (double)zv;
+                    }
                 }
             }
         }
     }
     if constexpr (RZ) {
         rz = block_sum(rz);
-        if (threadIdx.x == 0 && rz != 0.0) atomicAdd(&sc->rz[k], rz);
+        if (threadIdx.x == 0 && rz != 0.0) atomicAdd(rz_slot, rz);
     }
 }
 
@@ -774,15 +776,19 @@ static void launch_down(Ws& w, int l, cudaStream_t st) {
     down_kernel<<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.b, v.m, v.x, c.m, c.b, v.ny, v.nx, c.ny, c.nx, w.has_above,
                                                            w.has_below);
 }
-// rz_k >= 0 (level 0 only): the leg also accumulates rz[rz_k] = b . z
-static void launch_up(Ws& w, int l, cudaStream_t st, int rz_k = -1) {
+// where the level-0 up leg accumulates b . z (rows [lo, hi) of the level-0 grid); slot == nullptr: nowhere
+struct RzTarget {
+    double* slot = nullptr;
+    int64_t lo = 0, hi = 0;
+};
+static void launch_up(Ws& w, int l, cudaStream_t st, RzTarget rz = RzTarget()) {
     Level &v = w.lev[l], &c = w.lev[l + 1];
-    if (l == 0 && rz_k >= 0)
+    if (l == 0 && rz.slot)
         up_kernel<true><<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.x, c.y, v.b, v.m, v.y, v.ny, v.nx, c.nx, w.has_above,
-                                                                   w.has_below, w.sc, rz_k);
+                                                                   w.has_below, rz.slot, rz.lo, rz.hi);
     else
         up_kernel<false><<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.x, c.y, v.b, v.m, v.y, v.ny, v.nx, c.nx, w.has_above,
-                                                                    w.has_below, nullptr, 0);
+                                                                    w.has_below, nullptr, 0, 0);
 }
 
 // Parts of one V(3,3) cycle.  part 0: down legs of levels [0, split) (leaves lev[split].b);
@@ -791,7 +797,7 @@ static void launch_up(Ws& w, int l, cudaStream_t st, int rz_k = -1) {
 // is the whole cycle.  The row-band solver runs parts 0 and 2 on its band and part 1 on a
 // hierarchy of the global coarse grid that every rank holds (neilpy_b200/distributed.py).
 // Inside part 1 the levels from tail_level() on run in one launch (tail_kernel).
-static void vcycle_part(Ws& w, int split, int part, cudaStream_t st, int* launches, int rz_k = -1) {
+static void vcycle_part(Ws& w, int split, int part, cudaStream_t st, int* launches, RzTarget rz = RzTarget()) {
     const int L = w.nlev;
     if (split > L - 1) split = L - 1;
     int n = 0;
@@ -803,9 +809,9 @@ static void vcycle_part(Ws& w, int split, int part, cudaStream_t st, int* launch
         for (int l = split; l < lt; ++l, ++n) launch_down(w, l, st);
         tail_kernel<<<1, kTailThreads, 0, st>>>(w, lt);
         ++n;
-        for (int l = lt - 1; l >= split; --l, ++n) launch_up(w, l, st, rz_k);
+        for (int l = lt - 1; l >= split; --l, ++n) launch_up(w, l, st, rz);
     } else {
-        for (int l = split - 1; l >= 0; --l, ++n) launch_up(w, l, st, rz_k);
+        for (int l = split - 1; l >= 0; --l, ++n) launch_up(w, l, st, rz);
     }
     *launches += n;
 }
@@ -813,7 +819,9 @@ static void vcycle_part(Ws& w, int split, int part, cudaStream_t st, int* launch
 // z = M^-1 b0: one whole cycle; the level-0 result is left in lev[0].y.  rz_k >= 0: rz[rz_k] = b0 . z comes with it
 // (the level-0 up leg forms it), unless the hierarchy is a single level (then the caller runs rz_kernel).
 static const float* vcycle(Ws& w, cudaStream_t st, int* launches, int rz_k = -1) {
-    vcycle_part(w, 0, 1, st, launches, rz_k);
+    RzTarget rz;
+    if (rz_k >= 0) { rz.slot = &w.sc->rz[rz_k]; rz.lo = 0; rz.hi = w.lev[0].ny; }
+    vcycle_part(w, 0, 1, st, launches, rz);
     return w.lev[0].y;
 }
 static bool vcycle_forms_rz(const Ws& w) { return tail_level(w) >= 1 && w.nlev >= 2; }
@@ -1009,6 +1017,20 @@ int smrf_mg_cycle_part(int64_t ny, int64_t nx, void* workspace, size_t workspace
     if (int rc = check_ws("smrf_mg_cycle_part", workspace, workspace_bytes, ny, nx, has_above, has_below, &w)) return rc;
     int launches = 0;
     vcycle_part(w, split, part, (cudaStream_t)stream, &launches);
+    SMRF_LAUNCH_CHECK();
+    count_launches(launches);
+    return 0;
+}
+
+int smrf_mg_cycle_up_rz(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, int has_above, int has_below,
+                        int split, double* rz_slot, int64_t row_lo, int64_t row_hi, void* stream) {
+    SMRF_CHECK_ARG(split >= 1 && rz_slot && 0 <= row_lo && row_lo <= row_hi && row_hi <= ny, "bad split / rows / slot");
+    Ws w;
+    if (int rc = check_ws("smrf_mg_cycle_up_rz", workspace, workspace_bytes, ny, nx, has_above, has_below, &w)) return rc;
+    int launches = 0;
+    RzTarget rz;
+    rz.slot = rz_slot; rz.lo = row_lo; rz.hi = row_hi;
+    vcycle_part(w, split, 2, (cudaStream_t)stream, &launches, rz);
     SMRF_LAUNCH_CHECK();
     count_launches(launches);
     return 0;

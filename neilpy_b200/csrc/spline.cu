@@ -10,6 +10,8 @@
 // solve is done on a transposed copy.
 //
 // Classify: one thread per point, 16-tap gathers from the two coefficient grids (L2).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace smrf {

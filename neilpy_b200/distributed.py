@@ -196,8 +196,9 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
         e['cb'].copy_(e['full'][:e['nyG']])
         _lib.check(lib.smrf_mg_vcycle(e['nyG'], e['nxL'], api._ptr(e['wsC']), e['wsC'].numel(), st()), 'smrf_mg_vcycle')
         e['yLE'].copy_(e['cy'][e['g0']:e['g0'] + e['nyLE']])
-        _lib.check(lib.smrf_mg_cycle_part(e['nyE'], nx, wE, nE, e['haE'], e['hbE'], MG_SPLIT, 2, st()), 'mg up')
-        _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 20, z_ptr, None, None, None, None, st()), 'step20')
+        # up legs; the level-0 leg adds this band's share of r.z (its owned rows of the extended band) to rz[k]
+        _lib.check(lib.smrf_mg_cycle_up_rz(e['nyE'], nx, wE, nE, e['haE'], e['hbE'], MG_SPLIT, api._ptr(rz[k:k + 1]),
+                                           e['top'], e['top'] + ny, st()), 'mg up + rz')
 
     _lib.check(lib.smrf_inpaint_start(api._ptr(band), ny, nx, code, wp, wn, ha, hb, mean, api._ptr(guess), 0, None, None, st()), 'start0')
     u_above, u_below = exchange_halo(u, 1, group)
@@ -267,7 +268,15 @@ def _open_windows_band(lib, band, windows, thresholds, mask, when, negate, group
     rank, world = comm.rank, comm.world
     rows, nx = band.shape
     code, st = api._code(band.dtype), api._stream
-    cur = band
+    # rows padded to 16 bytes (as smrf_progressive_open pads its own surfaces): the marching kernels then take their
+    # TMA / vector paths whatever nx is; the padding travels with the halo rows and is never read as data
+    q = 4 if band.dtype == torch.float32 else 2
+    pitch = (nx + q - 1) // q * q
+    if pitch != nx:
+        cur = torch.zeros((rows, pitch), dtype=band.dtype, device=band.device)
+        cur[:, :nx] = band
+    else:
+        cur = band
     last = None
     min_rows = torch.tensor([rows], dtype=torch.int64, device=band.device)
     if world > 1:
@@ -284,6 +293,7 @@ def _open_windows_band(lib, band, windows, thresholds, mask, when, negate, group
         if when is not None:
             wbuf = torch.zeros((nb, nx), dtype=torch.uint8, device=band.device)
             wbuf[top:top + rows] = when
+        buf = buf.contiguous()
         a, b, tmp = buf, torch.empty_like(buf), torch.empty_like(buf)
         v0, v1 = 0, nb
         for i in chunk:
@@ -291,9 +301,9 @@ def _open_windows_band(lib, band, windows, thresholds, mask, when, negate, group
             v0 = v0 + 2 * w if top else 0
             v1 = v1 - 2 * w if bot else nb
             _lib.check(lib.smrf_open_window(api._ptr(a), api._ptr(b), api._ptr(tmp), api._ptr(mbuf), api._ptr(wbuf),
-                                            nb, nx, nx, code, w, float(thresholds[i]), i, int(negate), v0, v1, st()),
+                                            nb, nx, pitch, code, w, float(thresholds[i]), i, int(negate), v0, v1, st()),
                        'smrf_open_window')
-            last = b[top:top + rows]
+            last = b[top:top + rows, :nx]
             if len(windows) > 1:          # neilpy.py:1675-1676: last_surface advances only then
                 a, b = b, a
         mask.copy_(mbuf[top:top + rows])
