@@ -189,6 +189,14 @@ def _bin(lib, pts, dev, tdtype, cellsize, bin_type, edges):
 
 _pinned = {}
 _copy_pool = None
+_side_streams = {}
+
+
+def _side_stream(dev):
+    s = _side_streams.get(dev.index)
+    if s is None:
+        s = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return s
 
 
 def _copy_threads():
@@ -215,20 +223,37 @@ def _threaded_copy(dst, src):
     list(_copy_pool.map(lambda i: np.copyto(dst[cuts[i]:cuts[i + 1]], src[cuts[i]:cuts[i + 1]]), range(k)))
 
 
+class _HostCopy:
+    """Device tensor -> numpy through a cached pinned staging buffer (pageable D2H copies run at a fraction of the
+    link rate).  start() enqueues the D2H on `stream`; result() waits for it and copies the staging buffer into an
+    array the caller owns, so a copy started on a side stream overlaps the kernels that are still running."""
+
+    def __init__(self, t, stream=None):
+        self.shape = tuple(t.shape)
+        key = (t.dtype, t.numel(), 0 if stream is None else 1)
+        buf = _pinned.get(key)
+        if buf is None:
+            if len(_pinned) > 16:
+                _pinned.clear()
+            buf = _pinned[key] = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+        self.buf = buf
+        self.stream = stream if stream is not None else torch.cuda.current_stream()
+        self.src = t                      # keep the device tensor alive until the copy has run
+        with torch.cuda.stream(self.stream):
+            buf.copy_(t.reshape(-1), non_blocking=True)
+        self.done = torch.cuda.Event()
+        self.done.record(self.stream)
+
+    def result(self):
+        out = np.empty(self.buf.numel(), dtype=self.buf.numpy().dtype)         # pageable, owned by the caller
+        self.done.synchronize()
+        _threaded_copy(out, self.buf.numpy())
+        self.src = None
+        return out.reshape(self.shape)
+
+
 def _to_host(t):
-    """Device tensor -> numpy through a cached pinned staging buffer (pageable D2H copies run at
-    a fraction of the link rate)."""
-    key = (t.dtype, t.numel())
-    buf = _pinned.get(key)
-    if buf is None:
-        if len(_pinned) > 16:
-            _pinned.clear()
-        buf = _pinned[key] = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
-    buf.copy_(t.reshape(-1), non_blocking=True)
-    out = np.empty(t.numel(), dtype=buf.numpy().dtype)         # pageable, owned by the caller
-    torch.cuda.current_stream().synchronize()
-    _threaded_copy(out, buf.numpy())
-    return out.reshape(tuple(t.shape))
+    return _HostCopy(t).result()
 
 
 def _workspace(nbytes, dev):
@@ -428,6 +453,13 @@ def smrf(x, y=None, z=None, cellsize=1, windows=5, slope_threshold=.15, elevatio
         stages['Zpro_punched'] = Zpro.clone()
     info2 = _inpaint(lib, Zpro, ws, inpaint_tol, guess=opened)
     del opened
+    early = None
+    if not pts.on_device:
+        # host in -> host out: the DTM and the cell mask are final here; their D2H copies run on a side stream under
+        # the slope / spline / classification kernels that follow
+        side = _side_stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        early = (_HostCopy(Zpro, side), _HostCopy(object_cells, side))
     # --- slope raster (:1785-1786) and the two interpolating splines (:1773, :1788)
     S = torch.empty_like(Zpro)
     _lib.check(lib.smrf_slope(_ptr(Zpro), _ptr(S), ny, nx, code, float(cellsize), st), 'smrf_slope')
@@ -460,9 +492,10 @@ def smrf(x, y=None, z=None, cellsize=1, windows=5, slope_threshold=.15, elevatio
         zvals = pts.a[:, 2].to(torch.float64) if pts.fmt == _lib.PTS_XYZW_F32 else pts.z.to(torch.float64)
         extras = {'above_ground_height': zvals - elev, 'drop_raster': drop, 'when_dropped': when_pt}
     if not pts.on_device:
-        Zpro = _to_host(Zpro)
-        object_cells = _to_host(object_cells)
-        is_obj = _to_host(is_obj)
+        last = _HostCopy(is_obj)
+        Zpro = early[0].result()
+        object_cells = early[1].result().view(np.bool_)
+        is_obj = last.result().view(np.bool_)
         if pts.index is not None:
             import pandas as pd
             is_obj = pd.Series(is_obj, index=pts.index)
