@@ -230,15 +230,13 @@ def opening_roofline(torch, nb, Zsurf, reps, peaks):
     total_ms = float(per_w.sum())
     achieved = 18 * bytes_per_launch / (total_ms * 1e-3) / 1e9
     peak = peaks['hbm_gbs']
-    traffic = None                      # dram bytes per launch from the committed ncu capture of this grid, if any
-    tp = os.path.join(ROOT, 'profiles', 'r1_opening_traffic.json')
+    traffic = None                      # dram bytes per window, scaled from the committed ncu capture (8192 x 8192 grid)
+    tp = os.path.join(ROOT, 'profiles', 'r2_opening_traffic.json')
     if os.path.exists(tp):
-        g = json.load(open(tp))['grids'].get('%dx%d' % (ny, nx))
-        if g:
-            traffic = g['mean_bytes_per_launch']
+        traffic = json.load(open(tp))['mean_bytes_per_cell_window_w1_18'] * cells
     roof = {'bound': 'hbm', 'kernel': 'progressive opening W=1..18: open_march_kernel<W> (fused, W <= 6) and open_pass_kernel<W> x 2 (erosion + dilation, W >= 7); one CUDA-event interval per window', 'achieved': achieved,
             'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peaks['source'], 'traffic': traffic,
-            'traffic_source': 'STATIC: committed ncu capture profiles/r1_opening_traffic.json (dram__bytes_read+write, mean over the 18 launches of round 1; the round-2 two-pass kernels add the intermediate plane, see profiles/README.md)' if traffic else None,
+            'traffic_source': 'STATIC, not measured in this run: mean DRAM bytes per cell-window of the shipped kernels from the committed ncu capture profiles/r2_opening_traffic.json (8192 x 8192 grid), scaled to this grid' if traffic else None,
             'algorithmic_bytes_per_launch': bytes_per_launch, 'avg_launch_ms': total_ms / 18,
             'per_window_ms': [round(float(v), 4) for v in per_w],
             'per_window_frac': [round(float(bytes_per_launch / (v * 1e-3) / 1e9 / peak), 4) for v in per_w],
