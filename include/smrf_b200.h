@@ -139,6 +139,17 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
                  void* workspace, size_t workspace_bytes, double tol, int max_iter,
                  double* info_host, void* stream);
 
+/* ---- inpaint_nans_by_fda ------------------------------------- neilpy.py:1171-1216
+ * The "finite difference approximation" fill: one equation per cell whose stencil touches a NaN,
+ *   V (u[up] + u[down] - 2u) + H (u[left] + u[right] - 2u) = 0   (V = 1 on rows 1..ny-2, H = 1 on columns 1..nx-2),
+ * solved for the NaN cells in the least-squares sense (the reference calls LSQR), every equation weighted by the number
+ * of NaN cells its stencil touches (the reference's row selection repeats it that often).  Here: CGLS in float64, started
+ * from zero like LSQR; stops when max |A^T r| <= tol or after max_iter iterations.  NaN cells of `grid` are
+ * overwritten.  info_host = {iterations, final max |A^T r|, number of NaN cells}.  Synchronises `stream`. */
+size_t smrf_inpaint_fda_workspace_bytes(int64_t ny, int64_t nx);
+int smrf_inpaint_fda(void* grid, int64_t ny, int64_t nx, int dtype, void* workspace, size_t workspace_bytes,
+                     double tol, int max_iter, double* info_host, void* stream);
+
 /* The same solver, one phase at a time, for a row band whose neighbours live on other
  * ranks (the caller all-reduces the dot-product slots and exchanges one boundary row of u
  * (once) and of p (every iteration) between the calls -- neilpy_b200/distributed.py):

@@ -38,6 +38,8 @@ SIGNATURES = {
     'smrf_bin_accumulate_band': (_i32, [_vp, _vp, _vp, _i64, _i32, _dp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp]),
     'smrf_classify_band': (_i32, [_vp, _vp, _vp, _i64, _i32, _dp, _vp, _i64, _i64, _i64, _i64, _i32, _dbl, _dbl, _vp, _vp]),
     'smrf_inpaint_workspace_bytes': (_sz, [_i64, _i64]),
+    'smrf_inpaint_fda_workspace_bytes': (_sz, [_i64, _i64]),
+    'smrf_inpaint_fda': (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _dbl, _i32, _dp, _vp]),
     'smrf_inpaint_layout': (_i32, [_i64, _i64, C.POINTER(C.c_int64)]),
     'smrf_inpaint_setup': (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _i32, _i32, _vp]),
     'smrf_inpaint_start': (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _i32, _i32, _dbl, _vp, _i32, _vp, _vp, _vp]),

@@ -30,7 +30,8 @@ from . import _lib
 from . import spline as _spline
 from .affine import Affine
 
-__all__ = ['smrf', 'create_dem', 'progressive_filter', 'inpaint_nans_by_springs', 'Affine', 'InpaintWarning']
+__all__ = ['smrf', 'create_dem', 'progressive_filter', 'inpaint_nans_by_springs', 'inpaint_nans_by_fda', 'Affine',
+           'InpaintWarning']
 
 INPAINT_TOL = 1e-9       # metres, max-norm of the residual deg*u - sum(nbrs): <= 1e-6 m from the exact fill
 SMRF_INPAINT_TOL = 1e-6  # inside smrf(): residual max-norm; the fill ends <= ~1e-3 m from the exact one, 10x tighter than the reference's own LSQR (1.5e-2 m)
@@ -277,12 +278,12 @@ class InpaintWarning(RuntimeWarning):
     but a silently unconverged DTM would flow into the classification."""
 
 
-def _converged(info, tol):
+def _converged(info, tol, what='inpaint_nans_by_springs'):
     r = info['residual']
     info['converged'] = bool(info['unknown'] == 0 or (np.isfinite(r) and r <= tol))
     if not info['converged']:
-        warnings.warn('inpaint_nans_by_springs: residual %.3g m after %d iterations (tolerance %.3g m)%s'
-                      % (r, info['iterations'], tol, '' if np.isfinite(r) else ' -- non-finite elevations in the grid?'),
+        warnings.warn('%s: residual %.3g m after %d iterations (tolerance %.3g m)%s'
+                      % (what, r, info['iterations'], tol, '' if np.isfinite(r) else ' -- non-finite elevations in the grid?'),
                       InpaintWarning, stacklevel=3)
     return info
 
@@ -354,6 +355,45 @@ def inpaint_nans_by_springs(A, inplace=False, neighbors=4, tol=INPAINT_TOL, retu
     if g.dim() != 2:
         raise ValueError('A must be 2-D')
     info = _inpaint(lib, g, None, tol)
+    if inplace:
+        if isinstance(A, torch.Tensor):
+            if g.data_ptr() != A.data_ptr():
+                A.copy_(g)
+        else:
+            A[...] = g.cpu().numpy()
+        return None
+    out = g if on_device else g.cpu().numpy()
+    return (out, info) if return_info else out
+
+
+FDA_TOL = 1e-10          # max |A^T r| of the normal equations at which CGLS stops
+FDA_MAX_ITER = 60000
+
+
+def inpaint_nans_by_fda(A, fast=True, inplace=False, tol=FDA_TOL, return_info=False):
+    """neilpy.inpaint_nans_by_fda (neilpy.py:1171-1216): least-squares finite-difference fill of the NaN cells.
+    `fast` only prunes equations that cannot touch a NaN in the reference; the answer does not depend on it."""
+    lib, dev = _lib.load(), _device()
+    if isinstance(A, torch.Tensor):
+        on_device = A.is_cuda
+        if A.dtype not in (torch.float32, torch.float64):
+            raise ValueError('A must be float32 or float64')
+        g = (A.to(dev) if (inplace and on_device) else A.to(dev, copy=True)).contiguous()
+    else:
+        on_device = False
+        arr = np.asarray(A)
+        if arr.dtype != np.float32:
+            arr = arr.astype(np.float64, copy=False)
+        g = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+    if g.dim() != 2:
+        raise ValueError('A must be 2-D')
+    ny, nx = g.shape
+    ws = _workspace(lib.smrf_inpaint_fda_workspace_bytes(ny, nx), dev)
+    info = (C.c_double * 3)()
+    _lib.check(lib.smrf_inpaint_fda(_ptr(g), ny, nx, _code(g.dtype), _ptr(ws), ws.numel(), float(tol), FDA_MAX_ITER, info,
+                                    _stream()), 'smrf_inpaint_fda')
+    info = _converged({'iterations': int(info[0]), 'residual': float(info[1]), 'unknown': int(info[2])}, tol,
+                      'inpaint_nans_by_fda')
     if inplace:
         if isinstance(A, torch.Tensor):
             if g.data_ptr() != A.data_ptr():

@@ -31,7 +31,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 
 def _units():
     units = []
-    for name in ('rank', 'route', 'binning', 'grid_ops', 'inpaint', 'spline', 'las', 'terrain', 'opening_generic', 'opening_march'):
+    for name in ('rank', 'route', 'fda', 'binning', 'grid_ops', 'inpaint', 'spline', 'las', 'terrain', 'opening_generic', 'opening_march'):
         units.append((name + '.o', name + '.cu', []))
     for w in range(MARCH_MAX_W, 0, -1):   # slowest first
         units.append(('opening_march_w%02d.o' % w, 'opening_march_inst.cu', ['-DSMRF_W=%d' % w]))

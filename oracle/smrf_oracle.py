@@ -6,6 +6,7 @@ path of thomaspingel/neilpy so that the CUDA path can be checked against them:
     create_dem                 neilpy/neilpy.py:1110-1166
     unique_rows                neilpy/neilpy.py:1221-1224
     inpaint_nans_by_springs    neilpy/neilpy.py:1227-1271
+    inpaint_nans_by_fda        neilpy/neilpy.py:1171-1216
     progressive_filter         neilpy/neilpy.py:1659-1680
     smrf                       neilpy/neilpy.py:1685-1808
 
@@ -260,6 +261,64 @@ def harmonic_fill_exact(A):
     u = splinalg.spsolve(L.tocsc(), rhs)
     B = A.copy()
     B.ravel()[nan_list] = u
+    return B
+
+
+# --------------------------------------------------------------------------
+# neilpy.py:1171-1216  (the step after the path)
+# --------------------------------------------------------------------------
+def _fda_system(A, fast=True):
+    """The sparse system of inpaint_nans_by_fda exactly as the reference assembles it: returns (a, rhs_k, nan_list)."""
+    m, n = np.shape(A)
+    nanmat = np.isnan(A)
+    nan_list = np.flatnonzero(nanmat)
+    known_list = np.flatnonzero(~nanmat)
+    index = np.arange(m * n, dtype=np.int64).reshape((m, n))
+    i = np.hstack((np.tile(index[1:-1, :].ravel(), 3),
+                   np.tile(index[:, 1:-1].ravel(), 3)))
+    j = np.hstack((index[0:-2, :].ravel(),
+                   index[2:, :].ravel(),
+                   index[1:-1, :].ravel(),
+                   index[:, 0:-2].ravel(),
+                   index[:, 2:].ravel(),
+                   index[:, 1:-1].ravel()))
+    data = np.hstack((np.ones(2 * n * (m - 2), dtype=np.int64),
+                      -2 * np.ones(n * (m - 2), dtype=np.int64),
+                      np.ones(2 * m * (n - 2), dtype=np.int64),
+                      -2 * np.ones(m * (n - 2), dtype=np.int64)))
+    if fast == True:  # noqa: E712
+        goodrows = np.isin(i, index[ndi.binary_dilation(nanmat)])      # np.in1d in the reference (removed in numpy 2)
+        i = i[goodrows]
+        j = j[goodrows]
+        data = data[goodrows]
+    fda = sparse.coo_matrix((data, (i, j)), (m * n, m * n), dtype=np.int8).tocsr()
+    rhs = -fda[:, known_list] * A[np.unravel_index(known_list, (m, n))]
+    k = fda[:, np.unique(nan_list)]
+    k = k.nonzero()[0]
+    a = fda[k][:, nan_list]
+    return a, rhs[k], nan_list
+
+
+def inpaint_nans_by_fda(A, fast=True, inplace=False):
+    m, n = np.shape(A)
+    a, rhs, nan_list = _fda_system(A, fast)
+    results = splinalg.lsqr(a, rhs)[0]
+    if inplace:
+        A[np.unravel_index(nan_list, (m, n))] = results
+    else:
+        B = A.copy()
+        B[np.unravel_index(nan_list, (m, n))] = results
+        return B
+
+
+def fda_fill_exact(A):
+    """The exact least-squares fill the reference's LSQR approximates (tight LSQR on the same system)."""
+    m, n = np.shape(A)
+    a, rhs, nan_list = _fda_system(A, True)
+    B = A.copy()
+    if len(nan_list):
+        B[np.unravel_index(nan_list, (m, n))] = splinalg.lsqr(a.astype(np.float64), rhs, atol=1e-15, btol=1e-15,
+                                                              conlim=1e16, iter_lim=200000)[0]
     return B
 
 

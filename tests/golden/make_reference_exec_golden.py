@@ -5,7 +5,7 @@ SMRF path returns when it is executed in this container.
 
 `import neilpy` fails here (matplotlib, rasterio, skimage, ... are absent), but the five
 functions on the path -- unique_rows, inpaint_nans_by_springs, create_dem, progressive_filter,
-smrf (neilpy/neilpy.py:1110-1166, 1221-1271, 1659-1680, 1685-1808) -- only need numpy, pandas,
+smrf (neilpy/neilpy.py:1110-1166, 1221-1271, 1659-1680, 1685-1808), plus inpaint_nans_by_fda (:1171-1216) -- only need numpy, pandas,
 scipy and three third-party names.  Their source text is cut out of the reference module with
 `ast`, compiled and executed UNMODIFIED, with exactly those three names supplied by the
 oracle's restatements (and nothing else from the oracle):
@@ -35,7 +35,7 @@ sys.path.insert(0, os.path.join(HERE, '..', '..'))
 from oracle import smrf_oracle as O  # noqa: E402
 
 REF = '/root/reference/neilpy/neilpy.py'
-NAMES = ('unique_rows', 'inpaint_nans_by_springs', 'create_dem', 'progressive_filter', 'smrf')
+NAMES = ('unique_rows', 'inpaint_nans_by_springs', 'inpaint_nans_by_fda', 'create_dem', 'progressive_filter', 'smrf')
 NOTEBOOK = dict(cellsize=1, windows=18, slope_threshold=.15, elevation_threshold=.5, elevation_scaler=1.25)
 
 
@@ -93,6 +93,7 @@ def run(fns, x, y, z, kw):
     r['create_dem.max.inpaint'] = digest(Zmax)
     filled = fns['inpaint_nans_by_springs'](Zmin)
     r['inpaint_nans_by_springs'] = digest(filled)
+    r['inpaint_nans_by_fda'] = digest(fns['inpaint_nans_by_fda'](Zmin))          # neilpy.py:1171-1216
     w = kw['windows']
     w = np.arange(w) + 1 if np.isscalar(w) else w
     mask, when = fns['progressive_filter'](filled, w, cs, kw['slope_threshold'], return_when_dropped=True)
@@ -102,7 +103,7 @@ def run(fns, x, y, z, kw):
 
 def oracle_functions():
     return {'smrf': O.smrf, 'create_dem': O.create_dem, 'inpaint_nans_by_springs': O.inpaint_nans_by_springs,
-            'progressive_filter': O.progressive_filter}
+            'inpaint_nans_by_fda': O.inpaint_nans_by_fda, 'progressive_filter': O.progressive_filter}
 
 
 def main():

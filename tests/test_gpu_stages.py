@@ -251,6 +251,34 @@ def test_progressive_filter_isprs_grid(nb):
 
 
 # ------------------------------------------------------------------ inpaint
+def test_inpaint_fda_against_the_exact_least_squares_fill(nb):
+    """inpaint_nans_by_fda (neilpy.py:1171-1216): the CGLS fill equals the exact least-squares solution of the
+    reference's own system (<= 1e-6 m) and the reference's LSQR answer within LSQR's own tolerance."""
+    rng = np.random.default_rng(4)
+    yy, xx = np.meshgrid(np.arange(70.0), np.arange(95.0), indexing='ij')
+    Z = O.terrain(xx * 3, yy * 3) + rng.normal(0, 0.1, (70, 95))
+    A = Z.copy()
+    A[rng.random(A.shape) < 0.2] = np.nan
+    A[10:19, 20:33] = np.nan          # a block
+    A[0, 0] = np.nan                  # a corner (no equation of its own)
+    A[69, 5:9] = np.nan               # on the last row
+    A[30:34, 0] = np.nan              # on the first column
+    exact = O.fda_fill_exact(A)
+    ref = O.inpaint_nans_by_fda(A)
+    got, info = nb.inpaint_nans_by_fda(A, return_info=True)
+    assert info['converged'] and not np.isnan(got).any()
+    assert np.array_equal(got[~np.isnan(A)], A[~np.isnan(A)])
+    assert np.abs(got - exact).max() <= 1e-6, float(np.abs(got - exact).max())
+    assert np.abs(got - ref).max() <= 1e-3
+    # float32 grid, in place, no NaN, all NaN
+    got32 = nb.inpaint_nans_by_fda(A.astype(np.float32))
+    assert got32.dtype == np.float32 and np.abs(got32 - exact).max() <= 5e-5
+    B = A.copy()
+    assert nb.inpaint_nans_by_fda(B, inplace=True) is None and np.abs(B - exact).max() <= 1e-6
+    assert np.array_equal(nb.inpaint_nans_by_fda(Z), Z)
+    assert np.array_equal(nb.inpaint_nans_by_fda(np.full((9, 7), np.nan)), np.zeros((9, 7)))
+
+
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])
 def test_inpaint_against_exact_harmonic_fill(nb, dtype):
     rng = np.random.default_rng(11)
