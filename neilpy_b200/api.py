@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 import warnings
 
 import numpy as np
@@ -231,10 +232,11 @@ class _HostCopy:
 
     def __init__(self, t, stream=None):
         self.shape = tuple(t.shape)
-        key = (t.dtype, t.numel(), 0 if stream is None else 1)
+        # per thread (virtual ranks are threads of one process) and per role: a staging buffer is never shared
+        key = (t.dtype, t.numel(), 0 if stream is None else 1, threading.get_ident())
         buf = _pinned.get(key)
         if buf is None:
-            if len(_pinned) > 16:
+            if len(_pinned) > 32:
                 _pinned.clear()
             buf = _pinned[key] = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
         self.buf = buf

@@ -138,6 +138,18 @@ __device__ __forceinline__ int bspline4(double x, int n, double (&h)[4]) {
         l = (int)floor(x + 1.5);
         if (l > n - 1) l = n - 1;
     }
+    // Interior intervals (knots l-2 .. l+3 all of the arithmetic kind, spacing 1): the recurrence below collapses to
+    // the uniform cubic B-spline polynomials.  Same values to rounding (~1e-16 relative; the spline is held to 1e-9 m),
+    // without the recurrence's six divisions per axis -- the kernel is bound by its float64 arithmetic.
+    if (l >= 6 && l <= n - 4) {
+        const double u = x - ((double)l - 1.5), v = 1.0 - u;
+        const double u2 = u * u, u3 = u2 * u;
+        h[0] = v * v * v * (1.0 / 6.0);
+        h[1] = (3.0 * u3 - 6.0 * u2 + 4.0) * (1.0 / 6.0);
+        h[2] = (-3.0 * u3 + 3.0 * u2 + 3.0 * u + 1.0) * (1.0 / 6.0);
+        h[3] = u3 * (1.0 / 6.0);
+        return l;
+    }
     h[0] = 1.0; h[1] = 0.0; h[2] = 0.0; h[3] = 0.0;
 #pragma unroll
     for (int j = 1; j <= 3; ++j) {

@@ -480,6 +480,13 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     del opened
     del ws
     mark('inpaint2')
+    early = None
+    if not pts.on_device and not (gather and world > 1):
+        # host in -> host out: this band of the DTM and of the cell mask is final; copy it out on a side stream under
+        # the slope / spline / classification work that follows (as api.smrf does)
+        side = api._side_stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        early = (api._HostCopy(Zpro, side), api._HostCopy(object_cells, side))
 
     # ---- slope (1 halo row), spline coefficients (SPLINE_HALO rows), all-gather
     buf, top = with_halo(Zpro, 1, group)
@@ -525,6 +532,12 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     else:
         res['Zpro'], res['object_cells'] = Zpro, object_cells.view(torch.bool)
     if not pts.on_device:                                # host points in -> numpy out, like api.smrf
-        for k in ('Zpro', 'object_cells', 'is_object_point'):
-            res[k] = api._to_host(res[k])
+        if early is not None:
+            last = api._HostCopy(res['is_object_point'])
+            res['Zpro'] = early[0].result()
+            res['object_cells'] = early[1].result().view(np.bool_)
+            res['is_object_point'] = last.result()
+        else:
+            for k in ('Zpro', 'object_cells', 'is_object_point'):
+                res[k] = api._to_host(res[k])
     return res
