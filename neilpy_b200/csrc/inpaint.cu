@@ -473,47 +473,49 @@ __device__ __forceinline__ float jacobi(const float (*x)[kHX], const TileBuf& t,
 // Thread mapping of the fused legs: thread t owns column lx = t & 63 of the halo'd tile and the
 // rows ly = (t >> 6) + 4 e, e = 0..7, so everything that depends on the column only (in-grid
 // test, horizontal part of the degree, base address) is computed once per tile.
+template <typename I>
 struct TilePos {
     int lx, lyb;        // local column, first local row
     int y_first;        // grid row of local row lyb
     bool col_ok;        // column inside the grid
     int dxh;            // in-grid horizontal neighbours
-    int64_t g0;         // flat index of (y_first, column)
+    I g0;               // flat index of (y_first, column)
 };
-__device__ __forceinline__ TilePos tile_pos(int64_t y0, int64_t x0, int64_t nx) {
-    TilePos p;
+template <typename I>
+__device__ __forceinline__ TilePos<I> tile_pos(I y0, I x0, I nx) {
+    TilePos<I> p;
     p.lx = threadIdx.x & 63;
     p.lyb = threadIdx.x >> 6;
-    const int64_t xx = x0 + p.lx - kH;
+    const I xx = x0 + p.lx - kH;
     p.y_first = (int)(y0 - kH + p.lyb);
     p.col_ok = xx >= 0 && xx < nx;
     p.dxh = (xx > 0) + (xx + 1 < nx);
-    p.g0 = (int64_t)p.y_first * nx + xx;
+    p.g0 = (I)p.y_first * nx + xx;
     return p;
 }
 
 // loads b (and, on the way up, the iterate plus the coarse correction) of the halo'd tile;
 // fills t.b, t.dinv, t.deg, t.s0
-template <bool UP>
-__device__ __forceinline__ void load_tile(TileBuf& t, const TilePos& p, const float* __restrict__ b,
+template <bool UP, typename I>
+__device__ __forceinline__ void load_tile(TileBuf& t, const TilePos<I>& p, const float* __restrict__ b,
                                           const uint8_t* __restrict__ m, const float* __restrict__ x,
-                                          const float* __restrict__ xc, int ny, int64_t nx, int64_t cx, int above,
+                                          const float* __restrict__ xc, int ny, I nx, I cx, int above,
                                           int below) {
     uint8_t mm[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int y = p.y_first + 4 * e;
-        mm[e] = (p.col_ok && y >= 0 && y < ny) ? m[p.g0 + (int64_t)(4 * e) * nx] : 0;
+        mm[e] = (p.col_ok && y >= 0 && y < ny) ? m[p.g0 + (I)(4 * e) * nx] : 0;
     }
     float bb[8], xv[8], cv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const int64_t g = p.g0 + (int64_t)(4 * e) * nx;
+        const I g = p.g0 + (I)(4 * e) * nx;
         bb[e] = mm[e] ? b[g] : 0.f;
         if (UP) {
             const int y = p.y_first + 4 * e;
             xv[e] = mm[e] ? x[g] : 0.f;
-            cv[e] = mm[e] ? xc[(int64_t)(y >> 1) * cx + ((g - (int64_t)y * nx) >> 1)] : 0.f;
+            cv[e] = mm[e] ? xc[(I)(y >> 1) * cx + ((g - (I)y * nx) >> 1)] : 0.f;
         }
     }
 #pragma unroll
@@ -532,8 +534,8 @@ __device__ __forceinline__ void load_tile(TileBuf& t, const TilePos& p, const fl
 }
 
 // dst = jacobi(src, omega) on the tile plus `ring` rings
-template <int RING>
-__device__ __forceinline__ void sweep(float (*dst)[kHX], const float (*src)[kHX], const TileBuf& t, const TilePos& p,
+template <int RING, typename I>
+__device__ __forceinline__ void sweep(float (*dst)[kHX], const float (*src)[kHX], const TileBuf& t, const TilePos<I>& p,
                                       float omega) {
     constexpr int lo = kH - RING, hiy = kHY - 1 - (kH - RING), hix = kHX - 1 - (kH - RING);
     if (p.lx >= lo && p.lx <= hix) {
@@ -546,18 +548,22 @@ __device__ __forceinline__ void sweep(float (*dst)[kHX], const float (*src)[kHX]
 }
 
 // down leg: x = three Jacobi sweeps (weights A, B, C) from zero on A x = b;  bc = P^T (b - A x)
+// I: index type -- int when the level has fewer than 2^31 cells (all index arithmetic in 32 bits: the legs are
+// issue-bound and 64-bit multiplies / divides are instruction pairs and sequences), int64_t otherwise.
+template <typename I>
 __global__ void __launch_bounds__(kBlock) down_kernel(const float* __restrict__ b, const uint8_t* __restrict__ m,
                                                       float* __restrict__ xout, const uint8_t* __restrict__ mc,
-                                                      float* __restrict__ bc, int64_t ny, int64_t nx, int64_t cy,
-                                                      int64_t cx, int above, int below) {
+                                                      float* __restrict__ bc, int64_t ny_, int64_t nx_, int64_t cy_,
+                                                      int64_t cx_, int above, int below) {
     __shared__ TileBuf t;
-    const int64_t tiles_x = (nx + kTX - 1) / kTX, tiles = tiles_x * ((ny + kTY - 1) / kTY);
-    for (int64_t tile = tile_first(); tile < tiles; tile += tile_step()) {
-        const int64_t ty = tile / tiles_x;
-        const int64_t y0 = ty * kTY, x0 = (tile - ty * tiles_x) * kTX;
-        const TilePos p = tile_pos(y0, x0, nx);
+    const I ny = (I)ny_, nx = (I)nx_, cy = (I)cy_, cx = (I)cx_;
+    const I tiles_x = (nx + kTX - 1) / kTX, tiles = tiles_x * ((ny + kTY - 1) / kTY);
+    for (I tile = (I)tile_first(); tile < tiles; tile += (I)tile_step()) {
+        const I ty = tile / tiles_x;
+        const I y0 = ty * kTY, x0 = (tile - ty * tiles_x) * kTX;
+        const TilePos<I> p = tile_pos<I>(y0, x0, nx);
         __syncthreads();
-        load_tile<false>(t, p, b, m, nullptr, nullptr, (int)ny, nx, 0, above, below);
+        load_tile<false, I>(t, p, b, m, nullptr, nullptr, (int)ny, nx, (I)0, above, below);
         __syncthreads();
         sweep<2>(t.s1, t.s0, t, p, kOmegaB);
         __syncthreads();
@@ -567,13 +573,13 @@ __global__ void __launch_bounds__(kBlock) down_kernel(const float* __restrict__ 
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int ly = p.lyb + 4 * e, y = p.y_first + 4 * e;
-                if (ly >= kH && ly < kTY + kH && y < ny) xout[p.g0 + (int64_t)(4 * e) * nx] = t.s0[ly][p.lx];
+                if (ly >= kH && ly < kTY + kH && y < ny) xout[p.g0 + (I)(4 * e) * nx] = t.s0[ly][p.lx];
             }
         }
         // coarse right-hand side: 13 x 29 coarse cells per tile
         for (int i = threadIdx.x; i < (kTY / 2) * 32; i += kBlock) {
             const int cly = i >> 5, clx = i & 31;
-            const int64_t Y = y0 / 2 + cly, X = x0 / 2 + clx;
+            const I Y = y0 / 2 + cly, X = x0 / 2 + clx;
             if (clx < kTX / 2 && Y < cy && X < cx) {
                 float acc = 0.f;
                 if (mc[Y * cx + X]) {
@@ -596,20 +602,21 @@ __global__ void __launch_bounds__(kBlock) down_kernel(const float* __restrict__ 
 
 // up leg: x += P xc, then three Jacobi sweeps (weights C, B, A: the down leg's in reverse, which
 // keeps the cycle symmetric); written to `xout` (another buffer: tiles read each other's halo of x)
-template <bool RZ>
+template <bool RZ, typename I>
 __global__ void __launch_bounds__(kBlock) up_kernel(const float* __restrict__ x, const float* __restrict__ xc,
                                                     const float* __restrict__ b, const uint8_t* __restrict__ m,
-                                                    float* __restrict__ xout, int64_t ny, int64_t nx, int64_t cx,
+                                                    float* __restrict__ xout, int64_t ny_, int64_t nx_, int64_t cx_,
                                                     int above, int below, double* rz_slot, int64_t rz_lo, int64_t rz_hi) {
     __shared__ TileBuf t;
     double rz = 0.0;       // RZ (level 0): *rz_slot += b . z over rows [rz_lo, rz_hi) while z is at hand -- one pass less over the fine grid
-    const int64_t tiles_x = (nx + kTX - 1) / kTX, tiles = tiles_x * ((ny + kTY - 1) / kTY);
-    for (int64_t tile = tile_first(); tile < tiles; tile += tile_step()) {
-        const int64_t ty = tile / tiles_x;
-        const int64_t y0 = ty * kTY, x0 = (tile - ty * tiles_x) * kTX;
-        const TilePos p = tile_pos(y0, x0, nx);
+    const I ny = (I)ny_, nx = (I)nx_, cx = (I)cx_;
+    const I tiles_x = (nx + kTX - 1) / kTX, tiles = tiles_x * ((ny + kTY - 1) / kTY);
+    for (I tile = (I)tile_first(); tile < tiles; tile += (I)tile_step()) {
+        const I ty = tile / tiles_x;
+        const I y0 = ty * kTY, x0 = (tile - ty * tiles_x) * kTX;
+        const TilePos<I> p = tile_pos<I>(y0, x0, nx);
         __syncthreads();
-        load_tile<true>(t, p, b, m, x, xc, (int)ny, nx, cx, above, below);
+        load_tile<true, I>(t, p, b, m, x, xc, (int)ny, nx, cx, above, below);
         __syncthreads();
         sweep<2>(t.s1, t.s0, t, p, kOmegaC);
         __syncthreads();
@@ -621,7 +628,7 @@ __global__ void __launch_bounds__(kBlock) up_kernel(const float* __restrict__ x,
                 const int ly = p.lyb + 4 * e, y = p.y_first + 4 * e;
                 if (ly >= kH && ly < kTY + kH && y < ny) {
                     const float zv = jacobi(t.s0, t, ly, p.lx, kOmegaA);
-                    xout[p.g0 + (int64_t)(4 * e) * nx] = zv;
+                    xout[p.g0 + (I)(4 * e) * nx] = zv;
                     if constexpr (RZ) {
                         if (y >= rz_lo && y < rz_hi) rz += (double)t.b[ly][p.lx] * (double)zv;
                     }
@@ -773,8 +780,12 @@ static inline int tile_grid(int64_t ny, int64_t nx) {
 
 static void launch_down(Ws& w, int l, cudaStream_t st) {
     Level &v = w.lev[l], &c = w.lev[l + 1];
-    down_kernel<<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.b, v.m, v.x, c.m, c.b, v.ny, v.nx, c.ny, c.nx, w.has_above,
-                                                           w.has_below);
+    if (v.ny * v.nx < (int64_t)2000000000)
+        down_kernel<int><<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.b, v.m, v.x, c.m, c.b, v.ny, v.nx, c.ny, c.nx, w.has_above,
+                                                                    w.has_below);
+    else
+        down_kernel<int64_t><<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.b, v.m, v.x, c.m, c.b, v.ny, v.nx, c.ny, c.nx,
+                                                                        w.has_above, w.has_below);
 }
 // where the level-0 up leg accumulates b . z (rows [lo, hi) of the level-0 grid); slot == nullptr: nowhere
 struct RzTarget {
@@ -783,12 +794,18 @@ struct RzTarget {
 };
 static void launch_up(Ws& w, int l, cudaStream_t st, RzTarget rz = RzTarget()) {
     Level &v = w.lev[l], &c = w.lev[l + 1];
-    if (l == 0 && rz.slot)
-        up_kernel<true><<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.x, c.y, v.b, v.m, v.y, v.ny, v.nx, c.nx, w.has_above,
-                                                                   w.has_below, rz.slot, rz.lo, rz.hi);
-    else
-        up_kernel<false><<<fused_grid(v.ny, v.nx), kBlock, 0, st>>>(v.x, c.y, v.b, v.m, v.y, v.ny, v.nx, c.nx, w.has_above,
-                                                                    w.has_below, nullptr, 0, 0);
+    const bool small = v.ny * v.nx < (int64_t)2000000000;
+    const int g = fused_grid(v.ny, v.nx);
+#define SMRF_UP(RZ, I, SLOT, LO, HI) \
+    up_kernel<RZ, I><<<g, kBlock, 0, st>>>(v.x, c.y, v.b, v.m, v.y, v.ny, v.nx, c.nx, w.has_above, w.has_below, SLOT, LO, HI)
+    if (l == 0 && rz.slot) {
+        if (small) SMRF_UP(true, int, rz.slot, rz.lo, rz.hi);
+        else SMRF_UP(true, int64_t, rz.slot, rz.lo, rz.hi);
+    } else {
+        if (small) SMRF_UP(false, int, nullptr, 0, 0);
+        else SMRF_UP(false, int64_t, nullptr, 0, 0);
+    }
+#undef SMRF_UP
 }
 
 // Parts of one V(3,3) cycle.  part 0: down legs of levels [0, split) (leaves lev[split].b);
