@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
 namespace smrf {
@@ -54,6 +56,9 @@ struct Level {
 
 struct Ws {
     double *u, *r, *p, *q;
+    int *pos, *idx;          // compact CG: pos[cell] = index of the unknown (-1: known), idx[k] = cell of unknown k
+    void* scan_tmp;
+    size_t scan_tmp_bytes;
     Scalars* sc;
     int nlev;
     // row-band sharding: does a neighbouring band exist above row 0 / below row ny-1?  Its cells
@@ -72,6 +77,18 @@ static int level_dims(int64_t ny, int64_t nx, int64_t* lny, int64_t* lnx) {
         ny = (ny + 1) / 2; nx = (nx + 1) / 2;
     }
     return n;
+}
+
+// scratch of cub::DeviceScan over n flags; a generous bound when no device is present (size queries on a CPU box)
+static size_t scan_temp_bytes(size_t n) {
+    if (n >= ((size_t)1 << 31)) return 0;        // the compact path is not used for such grids
+    size_t bytes = 0;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint8_t*)nullptr, (int*)nullptr, (int)n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        bytes = n / 256 + ((size_t)1 << 20);
+    }
+    return bytes + 4096;
 }
 
 static size_t carve(void* workspace, int64_t ny, int64_t nx, Ws* w) {
@@ -95,6 +112,11 @@ static size_t carve(void* workspace, int64_t ny, int64_t nx, Ws* w) {
         t.lev[l].b = (float*)b; b += align_up(nl * 4);
     }
     t.sc = (Scalars*)b; b += align_up(sizeof(Scalars));
+    // appended last so that the offsets smrf_inpaint_layout reports never move: the index maps of the compact CG
+    // vectors (single-GPU solver) and the scratch of the prefix sum that builds them
+    t.pos = (int*)b; b += align_up(n * 4);
+    t.idx = (int*)b; b += align_up(n * 4);
+    t.scan_tmp = (void*)b; t.scan_tmp_bytes = scan_temp_bytes(n); b += align_up(t.scan_tmp_bytes);
     if (w) *w = t;
     return (size_t)(b - (char*)workspace);
 }
@@ -416,6 +438,128 @@ __global__ void __launch_bounds__(kBlock) update_kernel(Ws w, int64_t ny, int64_
     }
     rm = block_max(rm);
     if (threadIdx.x == 0) atomicMax(&w.sc->rmax[k + 1], (unsigned long long)__double_as_longlong(rm));
+}
+
+// ---- compact CG (single-GPU solver) -----------------------------------------------------------------------
+// Only 14 % (first solve) to ~30 % (second solve) of the cells are unknown, yet the grid-layout CG kernels stream
+// whole planes of u, r, p, q (the mask only predicates the accesses: at these densities nearly every 32-byte sector
+// is still touched).  Here the four float64 vectors hold the unknown cells only, in row-major order of the grid:
+// idx[k] is the cell of unknown k, pos[cell] its index (-1 for a known cell).  The V-cycle keeps the grid layout
+// (lev[0].b / lev[0].y): the residual is scattered into it by the update, the correction gathered from it by the
+// direction update.  The row-band solver keeps the grid-layout kernels (its halo exchanges address rows).
+__global__ void __launch_bounds__(kBlock) compact_build_kernel(const uint8_t* __restrict__ unk, int* __restrict__ pos,
+                                                               int* __restrict__ idx, int n) {
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        const int k = pos[i];               // exclusive prefix sum of the flags
+        if (unk[i]) idx[k] = i;
+        else pos[i] = -1;
+    }
+}
+
+// u_c = the caller's guess, else the mean of the known 4-neighbours, else the mean of all known cells
+template <typename T>
+__global__ void __launch_bounds__(kBlock) compact_init_kernel(const T* __restrict__ grid, Ws w, int ny, int nx, int nu,
+                                                              const T* __restrict__ guess) {
+    const double mean = w.sc->n_known ? w.sc->sum_known / (double)w.sc->n_known : 0.0;
+    for (int k = blockIdx.x * kBlock + threadIdx.x; k < nu; k += gridDim.x * kBlock) {
+        const int i = w.idx[k];
+        const int y = i / nx, x = i - y * nx;
+        double v = mean;
+        bool have = false;
+        if (guess) {
+            const double g = (double)guess[i];
+            if (g == g && fabs(g) < 1e300) { v = g; have = true; }   // a NaN / inf guess is ignored
+        }
+        if (!have) {
+            double s = 0.0;
+            int c = 0;
+            if (y > 0 && w.pos[i - nx] < 0) { s += (double)grid[i - nx]; ++c; }
+            if (y + 1 < ny && w.pos[i + nx] < 0) { s += (double)grid[i + nx]; ++c; }
+            if (x > 0 && w.pos[i - 1] < 0) { s += (double)grid[i - 1]; ++c; }
+            if (x + 1 < nx && w.pos[i + 1] < 0) { s += (double)grid[i + 1]; ++c; }
+            if (c) v = s / (double)c;
+        }
+        w.u[k] = v;
+    }
+}
+
+// value of the neighbour cell j in the current iterate: an unknown's u_c, else the grid value
+template <typename T>
+__device__ __forceinline__ double compact_val(const T* __restrict__ grid, const Ws& w, int j) {
+    const int pj = w.pos[j];
+    return pj >= 0 ? w.u[pj] : (double)grid[j];
+}
+
+// r_c = b - A u (the right-hand side is implicit in the known neighbours); lev[0].b = (float) r; p_c = 0; rmax[0]
+template <typename T>
+__global__ void __launch_bounds__(kBlock) compact_residual0_kernel(const T* __restrict__ grid, Ws w, int ny, int nx, int nu) {
+    double rm = 0.0;
+    for (int k = blockIdx.x * kBlock + threadIdx.x; k < nu; k += gridDim.x * kBlock) {
+        const int i = w.idx[k];
+        const int y = i / nx, x = i - y * nx;
+        double s = 0.0;
+        int d = 0;
+        if (y > 0) { s += compact_val(grid, w, i - nx); ++d; }
+        if (y + 1 < ny) { s += compact_val(grid, w, i + nx); ++d; }
+        if (x > 0) { s += compact_val(grid, w, i - 1); ++d; }
+        if (x + 1 < nx) { s += compact_val(grid, w, i + 1); ++d; }
+        const double r = d ? s - (double)d * w.u[k] : 0.0;
+        w.r[k] = r;
+        w.p[k] = 0.0;
+        w.lev[0].b[i] = (float)r;
+        rm = (fabs(r) < INFINITY) ? fmax(rm, fabs(r)) : INFINITY;     // a NaN / inf residual must surface
+    }
+    rm = block_max(rm);
+    if (threadIdx.x == 0) atomicMax(&w.sc->rmax[0], (unsigned long long)__double_as_longlong(rm));
+}
+
+// p_c = z + (rz[k] / rz[k-1]) p_c, z gathered from the grid-layout result of the cycle
+__global__ void __launch_bounds__(kBlock) compact_p_kernel(Ws w, const float* __restrict__ z, int nu, int k) {
+    const double beta = (k == 0 || w.sc->rz[k - 1] == 0.0) ? 0.0 : w.sc->rz[k] / w.sc->rz[k - 1];
+    for (int j = blockIdx.x * kBlock + threadIdx.x; j < nu; j += gridDim.x * kBlock)
+        w.p[j] = (double)z[w.idx[j]] + beta * w.p[j];
+}
+
+// q_c = A p_c; pq[k] = p . q
+__global__ void __launch_bounds__(kBlock) compact_apply_kernel(Ws w, int ny, int nx, int nu, int k) {
+    double pq = 0.0;
+    for (int j = blockIdx.x * kBlock + threadIdx.x; j < nu; j += gridDim.x * kBlock) {
+        const int i = w.idx[j];
+        const int y = i / nx, x = i - y * nx;
+        double s = 0.0;
+        int d = 0;
+        if (y > 0) { const int t = w.pos[i - nx]; if (t >= 0) s += w.p[t]; ++d; }
+        if (y + 1 < ny) { const int t = w.pos[i + nx]; if (t >= 0) s += w.p[t]; ++d; }
+        if (x > 0) { const int t = w.pos[i - 1]; if (t >= 0) s += w.p[t]; ++d; }
+        if (x + 1 < nx) { const int t = w.pos[i + 1]; if (t >= 0) s += w.p[t]; ++d; }
+        const double pj = w.p[j];
+        const double q = (double)d * pj - s;
+        w.q[j] = q;
+        pq += pj * q;
+    }
+    pq = block_sum(pq);
+    if (threadIdx.x == 0 && pq != 0.0) atomicAdd(&w.sc->pq[k], pq);
+}
+
+// u_c += alpha p_c; r_c -= alpha q_c; lev[0].b = (float) r; rmax[k+1] = max |r|
+__global__ void __launch_bounds__(kBlock) compact_update_kernel(Ws w, int nu, int k) {
+    const double pqk = w.sc->pq[k];
+    const double alpha = pqk != 0.0 ? w.sc->rz[k] / pqk : 0.0;
+    double rm = 0.0;
+    for (int j = blockIdx.x * kBlock + threadIdx.x; j < nu; j += gridDim.x * kBlock) {
+        const double rn = w.r[j] - alpha * w.q[j];
+        w.u[j] += alpha * w.p[j];
+        w.r[j] = rn;
+        w.lev[0].b[w.idx[j]] = (float)rn;
+        rm = (fabs(rn) < INFINITY) ? fmax(rm, fabs(rn)) : INFINITY;
+    }
+    rm = block_max(rm);
+    if (threadIdx.x == 0) atomicMax(&w.sc->rmax[k + 1], (unsigned long long)__double_as_longlong(rm));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) compact_writeback_kernel(T* __restrict__ grid, Ws w, int nu) {
+    for (int k = blockIdx.x * kBlock + threadIdx.x; k < nu; k += gridDim.x * kBlock) grid[w.idx[k]] = (T)w.u[k];
 }
 
 template <typename T>
@@ -1098,7 +1242,61 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
     if (unknown) SMRF_CUDA(cudaMemcpyAsync(unknown, w.lev[0].m, (size_t)n, cudaMemcpyDeviceToDevice, st));
     int it = 0;
     double rmax = 0.0;
-    if (n_unknown > 0) {
+    static const bool no_compact = []() { const char* e = getenv("SMRF_INPAINT_COMPACT"); return e && e[0] == '0'; }();
+    const bool compact = !jacobi && !no_compact && vcycle_forms_rz(w) && n < ((int64_t)1 << 31) && w.scan_tmp_bytes > 0;
+    if (n_unknown > 0 && compact) {
+        // ---- compact CG: u, r, p, q hold the unknown cells only (see compact_build_kernel)
+        const int nu = (int)n_unknown, ni = (int)n, iy = (int)ny, ix = (int)nx;
+        int64_t gc = ((int64_t)nu + kBlock - 1) / kBlock;
+        if (gc > (int64_t)num_sms() * 16) gc = (int64_t)num_sms() * 16;
+        const int g = (int)(gc < 1 ? 1 : gc), gn = g1_for(n);
+        size_t tb = w.scan_tmp_bytes;
+        SMRF_CUDA(cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, (const uint8_t*)w.lev[0].m, w.pos, ni, st));
+        compact_build_kernel<<<gn, kBlock, 0, st>>>(w.lev[0].m, w.pos, w.idx, ni);
+        SMRF_CUDA(cudaMemsetAsync(w.lev[0].b, 0, (size_t)n * sizeof(float), st));
+        if (dtype == SMRF_F32) {
+            compact_init_kernel<float><<<g, kBlock, 0, st>>>((const float*)grid, w, iy, ix, nu, (const float*)guess);
+            compact_residual0_kernel<float><<<g, kBlock, 0, st>>>((const float*)grid, w, iy, ix, nu);
+        } else {
+            compact_init_kernel<double><<<g, kBlock, 0, st>>>((const double*)grid, w, iy, ix, nu, (const double*)guess);
+            compact_residual0_kernel<double><<<g, kBlock, 0, st>>>((const double*)grid, w, iy, ix, nu);
+        }
+        SMRF_LAUNCH_CHECK();
+        int launches = 4;
+        unsigned long long bits = 0;
+        SMRF_CUDA(cudaMemcpyAsync(&bits, &w.sc->rmax[0], 8, cudaMemcpyDeviceToHost, st));
+        SMRF_CUDA(cudaStreamSynchronize(st));
+        memcpy(&rmax, &bits, 8);
+        double r_prev = rmax;
+        int it_prev = 0, burst = 4;
+        while (rmax > tol && it < max_iter) {
+            if (it + burst > max_iter) burst = max_iter - it;
+            for (int j = 0; j < burst; ++j, ++it) {
+                const float* z = vcycle(w, st, &launches, it);          // z = M^-1 r, rz[it] from the level-0 up leg
+                compact_p_kernel<<<g, kBlock, 0, st>>>(w, z, nu, it);
+                compact_apply_kernel<<<g, kBlock, 0, st>>>(w, iy, ix, nu, it);
+                compact_update_kernel<<<g, kBlock, 0, st>>>(w, nu, it);
+                launches += 3;
+            }
+            SMRF_LAUNCH_CHECK();
+            SMRF_CUDA(cudaMemcpyAsync(&bits, &w.sc->rmax[it], 8, cudaMemcpyDeviceToHost, st));
+            SMRF_CUDA(cudaStreamSynchronize(st));
+            memcpy(&rmax, &bits, 8);
+            if (!(rmax < INFINITY)) break;   // NaN / inf: give up rather than spin (the caller reports it)
+            int next = kCheckEvery;
+            if (rmax > tol && rmax > 0.0 && rmax < r_prev && it > it_prev) {
+                const double rate = (log(rmax) - log(r_prev)) / (double)(it - it_prev);   // < 0
+                const double left = (log(tol) - log(rmax)) / rate;
+                next = left < 1.0 ? 1 : (left > (double)kCheckEvery ? kCheckEvery : (int)ceil(left));
+            }
+            r_prev = rmax; it_prev = it; burst = next;
+        }
+        if (dtype == SMRF_F32) compact_writeback_kernel<float><<<g, kBlock, 0, st>>>((float*)grid, w, nu);
+        else compact_writeback_kernel<double><<<g, kBlock, 0, st>>>((double*)grid, w, nu);
+        SMRF_LAUNCH_CHECK();
+        count_launches(launches + 1);
+        SMRF_CUDA(cudaStreamSynchronize(st));
+    } else if (n_unknown > 0) {
         const double mean = stats.nk ? stats.sum / (double)stats.nk : 0.0;
         if (int rc = smrf_inpaint_start(grid, ny, nx, dtype, workspace, workspace_bytes, 0, 0, mean, guess, 0, nullptr, nullptr, stream)) return rc;
         if (int rc = smrf_inpaint_start(grid, ny, nx, dtype, workspace, workspace_bytes, 0, 0, mean, nullptr, 1, nullptr, nullptr, stream)) return rc;
