@@ -177,6 +177,20 @@ int smrf_inpaint_start(const void* grid, int64_t ny, int64_t nx, int dtype, void
 int smrf_inpaint_step(int64_t ny, int64_t nx, void* workspace, size_t workspace_bytes, int has_above,
                       int has_below, int k, int phase, const float* z_ext, const double* p_above,
                       const double* p_below, const uint8_t* m_above, const uint8_t* m_below, void* stream);
+/* The row-band solver with COMPACT CG vectors (u, r, p, q hold the band's NaN cells only, as smrf_inpaint does on
+ * one GPU); replaces smrf_inpaint_start / _step phases 1-3 / _finish after smrf_inpaint_setup.  op:
+ *   0  index maps + zeroed float32 residual plane        1  starting guess (`guess`, `guess_grid`)
+ *   2  out_first / out_last = boundary rows of u (known elevations included) for the neighbours
+ *   3  r = b - A u with row_above / row_below (the neighbours' rows of u), rmax[0]
+ *   4  p = z + (rz[k]/rz[k-1]) p, then out_first / out_last = boundary rows of p (0 on known cells)
+ *   5  q = A p with row_above / row_below (the neighbours' rows of p), pq[k] += p.q
+ *   6  u += alpha p, r -= alpha q, float32 residual plane (level-0 right-hand side of the cycle), rmax[k+1]
+ *   7  write the solution into the NaN cells of `grid`
+ * n_unknown = this band's NaN cells (statistics block of smrf_inpaint_setup, before any all-reduce). */
+int smrf_inpaint_compact(int op, const void* grid, int64_t ny, int64_t nx, int dtype, void* workspace,
+                         size_t workspace_bytes, int has_above, int has_below, int64_t n_unknown, int k, double guess,
+                         const void* guess_grid, const float* z, const double* row_above, const double* row_below,
+                         double* out_first, double* out_last, void* stream);
 /* Preconditioning a row band with the GLOBAL V-cycle.  A band-local cycle (any closure at the band
  * edge) mistreats every error mode that is smooth across the edge and costs ~60 % more CG
  * iterations; instead the caller (neilpy_b200/distributed.py)

@@ -491,8 +491,11 @@ __device__ __forceinline__ double compact_val(const T* __restrict__ grid, const 
 }
 
 // r_c = b - A u (the right-hand side is implicit in the known neighbours); lev[0].b = (float) r; p_c = 0; rmax[0]
+// (row bands: ua / ub = the neighbouring bands' boundary rows of u, known values included)
 template <typename T>
-__global__ void __launch_bounds__(kBlock) compact_residual0_kernel(const T* __restrict__ grid, Ws w, int ny, int nx, int nu) {
+__global__ void __launch_bounds__(kBlock) compact_residual0_kernel(const T* __restrict__ grid, Ws w, int ny, int nx, int nu,
+                                                                   const double* __restrict__ ua,
+                                                                   const double* __restrict__ ub) {
     double rm = 0.0;
     for (int k = blockIdx.x * kBlock + threadIdx.x; k < nu; k += gridDim.x * kBlock) {
         const int i = w.idx[k];
@@ -500,7 +503,9 @@ __global__ void __launch_bounds__(kBlock) compact_residual0_kernel(const T* __re
         double s = 0.0;
         int d = 0;
         if (y > 0) { s += compact_val(grid, w, i - nx); ++d; }
+        else if (w.has_above) { s += ua[x]; ++d; }
         if (y + 1 < ny) { s += compact_val(grid, w, i + nx); ++d; }
+        else if (w.has_below) { s += ub[x]; ++d; }
         if (x > 0) { s += compact_val(grid, w, i - 1); ++d; }
         if (x + 1 < nx) { s += compact_val(grid, w, i + 1); ++d; }
         const double r = d ? s - (double)d * w.u[k] : 0.0;
@@ -513,6 +518,20 @@ __global__ void __launch_bounds__(kBlock) compact_residual0_kernel(const T* __re
     if (threadIdx.x == 0) atomicMax(&w.sc->rmax[0], (unsigned long long)__double_as_longlong(rm));
 }
 
+// first and last row of a compact vector as dense rows for the halo exchange of the row-band solver: the unknown's
+// value, else `grid` (u: the known elevation) or 0 (p: no search direction on known cells)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) compact_rows_kernel(const double* __restrict__ v, const T* __restrict__ grid, Ws w,
+                                                              int ny, int nx, double* __restrict__ first,
+                                                              double* __restrict__ last) {
+    for (int x = blockIdx.x * kBlock + threadIdx.x; x < nx; x += gridDim.x * kBlock) {
+        const int i0 = x, i1 = (ny - 1) * nx + x;
+        const int p0 = w.pos[i0], p1 = w.pos[i1];
+        if (first) first[x] = p0 >= 0 ? v[p0] : (grid ? (double)grid[i0] : 0.0);
+        if (last) last[x] = p1 >= 0 ? v[p1] : (grid ? (double)grid[i1] : 0.0);
+    }
+}
+
 // p_c = z + (rz[k] / rz[k-1]) p_c, z gathered from the grid-layout result of the cycle
 __global__ void __launch_bounds__(kBlock) compact_p_kernel(Ws w, const float* __restrict__ z, int nu, int k) {
     const double beta = (k == 0 || w.sc->rz[k - 1] == 0.0) ? 0.0 : w.sc->rz[k] / w.sc->rz[k - 1];
@@ -521,7 +540,9 @@ __global__ void __launch_bounds__(kBlock) compact_p_kernel(Ws w, const float* __
 }
 
 // q_c = A p_c; pq[k] = p . q
-__global__ void __launch_bounds__(kBlock) compact_apply_kernel(Ws w, int ny, int nx, int nu, int k) {
+// (row bands: pa / pb = the neighbouring bands' boundary rows of p, zero at their known cells)
+__global__ void __launch_bounds__(kBlock) compact_apply_kernel(Ws w, int ny, int nx, int nu, int k,
+                                                               const double* __restrict__ pa, const double* __restrict__ pb) {
     double pq = 0.0;
     for (int j = blockIdx.x * kBlock + threadIdx.x; j < nu; j += gridDim.x * kBlock) {
         const int i = w.idx[j];
@@ -529,7 +550,9 @@ __global__ void __launch_bounds__(kBlock) compact_apply_kernel(Ws w, int ny, int
         double s = 0.0;
         int d = 0;
         if (y > 0) { const int t = w.pos[i - nx]; if (t >= 0) s += w.p[t]; ++d; }
+        else if (w.has_above) { s += pa[x]; ++d; }
         if (y + 1 < ny) { const int t = w.pos[i + nx]; if (t >= 0) s += w.p[t]; ++d; }
+        else if (w.has_below) { s += pb[x]; ++d; }
         if (x > 0) { const int t = w.pos[i - 1]; if (t >= 0) s += w.p[t]; ++d; }
         if (x + 1 < nx) { const int t = w.pos[i + 1]; if (t >= 0) s += w.p[t]; ++d; }
         const double pj = w.p[j];
@@ -1222,6 +1245,84 @@ int smrf_inpaint_finish(void* grid, int64_t ny, int64_t nx, int dtype, void* wor
     return 0;
 }
 
+// The compact solver, one phase at a time, for a row band (neilpy_b200/distributed.py); see include/smrf_b200.h.
+int smrf_inpaint_compact(int op, const void* grid, int64_t ny, int64_t nx, int dtype, void* workspace, size_t workspace_bytes,
+                         int has_above, int has_below, int64_t n_unknown, int k, double guess, const void* guess_grid,
+                         const float* z, const double* row_above, const double* row_below, double* out_first,
+                         double* out_last, void* stream) {
+    SMRF_CHECK_ARG(dtype == SMRF_F32 || dtype == SMRF_F64, "bad dtype");
+    SMRF_CHECK_ARG(ny > 0 && nx > 0 && ny * nx < ((int64_t)1 << 31), "grid too large for the compact solver");
+    SMRF_CHECK_ARG(n_unknown >= 0 && n_unknown <= ny * nx && k >= 0 && k < kMaxIter, "bad n_unknown / iteration");
+    Ws w;
+    if (int rc = check_ws("smrf_inpaint_compact", workspace, workspace_bytes, ny, nx, has_above, has_below, &w)) return rc;
+    SMRF_CHECK_ARG(w.scan_tmp_bytes > 0, "no scan scratch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = ny * nx;
+    const int nu = (int)n_unknown, ni = (int)n, iy = (int)ny, ix = (int)nx;
+    int64_t gc = ((int64_t)nu + kBlock - 1) / kBlock;
+    if (gc > (int64_t)num_sms() * 16) gc = (int64_t)num_sms() * 16;
+    const int g = (int)(gc < 1 ? 1 : gc);
+    const int gr = (int)((nx + kBlock - 1) / kBlock);
+    int launches = 1;
+    switch (op) {
+        case 0: {   // index maps (after smrf_inpaint_setup) and a zeroed float32 residual plane
+            size_t tb = w.scan_tmp_bytes;
+            SMRF_CUDA(cub::DeviceScan::ExclusiveSum(w.scan_tmp, tb, (const uint8_t*)w.lev[0].m, w.pos, ni, st));
+            compact_build_kernel<<<g1_for(n), kBlock, 0, st>>>(w.lev[0].m, w.pos, w.idx, ni);
+            SMRF_CUDA(cudaMemsetAsync(w.lev[0].b, 0, (size_t)n * sizeof(float), st));
+            launches = 2;
+            break;
+        }
+        case 1: {   // starting guess (the mean of the known cells travels in the statistics block, as in smrf_inpaint_start)
+            SMRF_CHECK_ARG(grid, "null grid");
+            unsigned long long one = 1;
+            SMRF_CUDA(cudaMemcpyAsync(&w.sc->sum_known, &guess, 8, cudaMemcpyHostToDevice, st));
+            SMRF_CUDA(cudaMemcpyAsync(&w.sc->n_known, &one, 8, cudaMemcpyHostToDevice, st));
+            if (nu == 0) { launches = 0; break; }
+            if (dtype == SMRF_F32) compact_init_kernel<float><<<g, kBlock, 0, st>>>((const float*)grid, w, iy, ix, nu, (const float*)guess_grid);
+            else compact_init_kernel<double><<<g, kBlock, 0, st>>>((const double*)grid, w, iy, ix, nu, (const double*)guess_grid);
+            break;
+        }
+        case 2:     // boundary rows of u (known values included) for the neighbours
+            SMRF_CHECK_ARG(grid, "null grid");
+            if (dtype == SMRF_F32) compact_rows_kernel<float><<<gr, kBlock, 0, st>>>(w.u, (const float*)grid, w, iy, ix, out_first, out_last);
+            else compact_rows_kernel<double><<<gr, kBlock, 0, st>>>(w.u, (const double*)grid, w, iy, ix, out_first, out_last);
+            break;
+        case 3:     // r = b - A u with the neighbours' rows of u, rmax[0]
+            SMRF_CHECK_ARG(grid && (!has_above || row_above) && (!has_below || row_below), "missing halo row of u");
+            if (nu == 0) { launches = 0; break; }
+            if (dtype == SMRF_F32) compact_residual0_kernel<float><<<g, kBlock, 0, st>>>((const float*)grid, w, iy, ix, nu, row_above, row_below);
+            else compact_residual0_kernel<double><<<g, kBlock, 0, st>>>((const double*)grid, w, iy, ix, nu, row_above, row_below);
+            break;
+        case 4:     // p = z + beta p (rz[k] complete), then its boundary rows for the neighbours
+            SMRF_CHECK_ARG(z, "null z");
+            if (nu) compact_p_kernel<<<g, kBlock, 0, st>>>(w, z, nu, k);
+            compact_rows_kernel<float><<<gr, kBlock, 0, st>>>(w.p, nullptr, w, iy, ix, out_first, out_last);
+            launches = 2;
+            break;
+        case 5:     // q = A p with the neighbours' rows of p, pq[k]
+            SMRF_CHECK_ARG((!has_above || row_above) && (!has_below || row_below), "missing halo row of p");
+            if (nu == 0) { launches = 0; break; }
+            compact_apply_kernel<<<g, kBlock, 0, st>>>(w, iy, ix, nu, k, row_above, row_below);
+            break;
+        case 6:     // u += alpha p, r -= alpha q (pq[k] complete), rmax[k+1]
+            if (nu == 0) { launches = 0; break; }
+            compact_update_kernel<<<g, kBlock, 0, st>>>(w, nu, k);
+            break;
+        case 7:     // the solution into the NaN cells of the grid
+            SMRF_CHECK_ARG(grid, "null grid");
+            if (nu == 0) { launches = 0; break; }
+            if (dtype == SMRF_F32) compact_writeback_kernel<float><<<g, kBlock, 0, st>>>((float*)const_cast<void*>(grid), w, nu);
+            else compact_writeback_kernel<double><<<g, kBlock, 0, st>>>((double*)const_cast<void*>(grid), w, nu);
+            break;
+        default:
+            SMRF_CHECK_ARG(false, "bad op");
+    }
+    SMRF_LAUNCH_CHECK();
+    count_launches(launches);
+    return 0;
+}
+
 int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown, const void* guess, void* workspace,
                  size_t workspace_bytes, double tol, int max_iter, double* info_host, void* stream) {
     SMRF_CHECK_ARG(grid && workspace, "null pointer");
@@ -1256,10 +1357,10 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
         SMRF_CUDA(cudaMemsetAsync(w.lev[0].b, 0, (size_t)n * sizeof(float), st));
         if (dtype == SMRF_F32) {
             compact_init_kernel<float><<<g, kBlock, 0, st>>>((const float*)grid, w, iy, ix, nu, (const float*)guess);
-            compact_residual0_kernel<float><<<g, kBlock, 0, st>>>((const float*)grid, w, iy, ix, nu);
+            compact_residual0_kernel<float><<<g, kBlock, 0, st>>>((const float*)grid, w, iy, ix, nu, nullptr, nullptr);
         } else {
             compact_init_kernel<double><<<g, kBlock, 0, st>>>((const double*)grid, w, iy, ix, nu, (const double*)guess);
-            compact_residual0_kernel<double><<<g, kBlock, 0, st>>>((const double*)grid, w, iy, ix, nu);
+            compact_residual0_kernel<double><<<g, kBlock, 0, st>>>((const double*)grid, w, iy, ix, nu, nullptr, nullptr);
         }
         SMRF_LAUNCH_CHECK();
         int launches = 4;
@@ -1274,7 +1375,7 @@ int smrf_inpaint(void* grid, int64_t ny, int64_t nx, int dtype, uint8_t* unknown
             for (int j = 0; j < burst; ++j, ++it) {
                 const float* z = vcycle(w, st, &launches, it);          // z = M^-1 r, rz[it] from the level-0 up leg
                 compact_p_kernel<<<g, kBlock, 0, st>>>(w, z, nu, it);
-                compact_apply_kernel<<<g, kBlock, 0, st>>>(w, iy, ix, nu, it);
+                compact_apply_kernel<<<g, kBlock, 0, st>>>(w, iy, ix, nu, it, nullptr, nullptr);
                 compact_update_kernel<<<g, kBlock, 0, st>>>(w, nu, it);
                 launches += 3;
             }

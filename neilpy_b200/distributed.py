@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -127,8 +128,10 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
 
     _lib.check(lib.smrf_inpaint_setup(api._ptr(band), ny, nx, code, wp, wn, ha, hb, st()), 'smrf_inpaint_setup')
     stats = torch.stack([f64(off_stats, 1)[0], i64(off_stats + 8, 2)[0].double(), i64(off_stats + 8, 2)[1].double()])
+    mine = stats[2:3].clone()                      # this band's own NaN cells (length of its compact CG vectors)
     comm.all_reduce(stats)
-    s_known, n_known, n_unknown = [float(v) for v in stats.cpu()]
+    s_known, n_known, n_unknown, nu = [float(v) for v in torch.cat([stats, mine]).cpu()]
+    nu = int(nu)
     info = {'iterations': 0, 'residual': 0.0, 'unknown': int(n_unknown)}
     if n_unknown == 0:
         return info, ws
@@ -200,10 +203,31 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
         _lib.check(lib.smrf_mg_cycle_up_rz(e['nyE'], nx, wE, nE, e['haE'], e['hbE'], MG_SPLIT, api._ptr(rz[k:k + 1]),
                                            e['top'], e['top'] + ny, st()), 'mg up + rz')
 
-    _lib.check(lib.smrf_inpaint_start(api._ptr(band), ny, nx, code, wp, wn, ha, hb, mean, api._ptr(guess), 0, None, None, st()), 'start0')
-    u_above, u_below = exchange_halo(u, 1, group)
-    _lib.check(lib.smrf_inpaint_start(api._ptr(band), ny, nx, code, wp, wn, ha, hb, mean, None, 1, api._ptr(u_above),
-                                      api._ptr(u_below), st()), 'start1')
+    # With the global preconditioner the CG vectors are COMPACT (this band's NaN cells only, as on one GPU): the
+    # V-cycle reads the float32 residual plane the update scatters and hands back z in the grid layout, and only
+    # the two boundary rows of u / p are expanded to dense rows for the neighbours.
+    compact = ext is not None and ny * nx < 2 ** 31 and os.environ.get('SMRF_INPAINT_COMPACT', '1') != '0'
+    bp = api._ptr(band)
+    if compact:
+        rows = torch.empty((4, nx), dtype=torch.float64, device=band.device)
+        first, last = rows[0:1], rows[1:2]
+
+        def cg(op, k=0, z=None, above=None, below=None, outs=False, what='compact'):
+            _lib.check(lib.smrf_inpaint_compact(op, bp, ny, nx, code, wp, wn, ha, hb, nu, k, mean,
+                                                api._ptr(guess) if op == 1 else None, z, api._ptr(above), api._ptr(below),
+                                                api._ptr(first) if outs else None, api._ptr(last) if outs else None, st()),
+                       'smrf_inpaint_compact(%s)' % what)
+
+        cg(0, what='maps')
+        cg(1, what='guess')
+        cg(2, outs=True, what='rows of u')
+        u_above, u_below = comm.exchange(first if ha else None, last if hb else None)
+        cg(3, above=u_above, below=u_below, what='residual')
+    else:
+        _lib.check(lib.smrf_inpaint_start(bp, ny, nx, code, wp, wn, ha, hb, mean, api._ptr(guess), 0, None, None, st()), 'start0')
+        u_above, u_below = exchange_halo(u, 1, group)
+        _lib.check(lib.smrf_inpaint_start(bp, ny, nx, code, wp, wn, ha, hb, mean, None, 1, api._ptr(u_above),
+                                          api._ptr(u_below), st()), 'start1')
 
     def residual(k):
         comm.all_reduce(rmax[k:k + 1], 'max')
@@ -216,6 +240,14 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
             k = it
             precondition(k)
             comm.all_reduce(rz[k:k + 1])
+            if compact:
+                cg(4, k, z=z_ptr, outs=True, what='direction')
+                p_above, p_below = comm.exchange(first if ha else None, last if hb else None)
+                cg(5, k, above=p_above, below=p_below, what='apply')
+                comm.all_reduce(pq[k:k + 1])
+                cg(6, k, what='update')
+                it += 1
+                continue
             _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 1, z_ptr, None, None, None, None, st()), 'step1')
             p_above, p_below = exchange_halo(p, 1, group)
             _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 2, None, api._ptr(p_above), api._ptr(p_below),
@@ -232,7 +264,10 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
             left = (math.log(tol) - math.log(r)) / rate
             nxt = 1 if left < 1 else (8 if left > 8 else int(math.ceil(left)))
         r_prev, it_prev, burst = r, it, nxt
-    _lib.check(lib.smrf_inpaint_finish(api._ptr(band), ny, nx, code, wp, wn, st()), 'smrf_inpaint_finish')
+    if compact:
+        cg(7, what='write back')
+    else:
+        _lib.check(lib.smrf_inpaint_finish(bp, ny, nx, code, wp, wn, st()), 'smrf_inpaint_finish')
     info.update(iterations=it, residual=r)
     return api._converged(info, tol), ws
 
