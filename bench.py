@@ -373,6 +373,12 @@ def run_gpu(args):
         os.environ['SMRF_TIMING'] = '1'
         stage_ms = smrf_sharded(pts, **PARAMS)['info']['timing_ms']
         os.environ.pop('SMRF_TIMING', None)
+        # and the sections of the CG iterations of the two solves (CUDA events on the stream, no extra synchronisation)
+        os.environ['SMRF_TIMING_ITER'] = '1'
+        inf = smrf_sharded(pts, **PARAMS)['info']
+        os.environ.pop('SMRF_TIMING_ITER', None)
+        stage_ms = dict(stage_ms, cg_sections_ms={k: inf[k].get('sections_ms') for k in ('inpaint1', 'inpaint2')},
+                        cg_iterations=[inf['inpaint1']['iterations'], inf['inpaint2']['iterations']])
 
     # ---- the float64 arm (the reference's own dtype: float64 x, y, z -> float64 grids; the opening runs in rank space)
     f64 = None

@@ -186,11 +186,13 @@ int smrf_inpaint_step(int64_t ny, int64_t nx, void* workspace, size_t workspace_
  *   5  q = A p with row_above / row_below (the neighbours' rows of p), pq[k] += p.q
  *   6  u += alpha p, r -= alpha q, float32 residual plane (level-0 right-hand side of the cycle), rmax[k+1]
  *   7  write the solution into the NaN cells of `grid`
- * n_unknown = this band's NaN cells (statistics block of smrf_inpaint_setup, before any all-reduce). */
+ * n_unknown = this band's NaN cells (statistics block of smrf_inpaint_setup, before any all-reduce).
+ * r_plane (ops 0, 3, 6; may be NULL) = where the float32 residual plane lives instead of the workspace's own
+ * level-0 right-hand side: ny x nx floats, e.g. the owned rows of the ghost-extended band smrf_mg_cycle_part reads. */
 int smrf_inpaint_compact(int op, const void* grid, int64_t ny, int64_t nx, int dtype, void* workspace,
                          size_t workspace_bytes, int has_above, int has_below, int64_t n_unknown, int k, double guess,
-                         const void* guess_grid, const float* z, const double* row_above, const double* row_below,
-                         double* out_first, double* out_last, void* stream);
+                         const void* guess_grid, const float* z, float* r_plane, const double* row_above,
+                         const double* row_below, double* out_first, double* out_last, void* stream);
 /* Preconditioning a row band with the GLOBAL V-cycle.  A band-local cycle (any closure at the band
  * edge) mistreats every error mode that is smooth across the edge and costs ~60 % more CG
  * iterations; instead the caller (neilpy_b200/distributed.py)

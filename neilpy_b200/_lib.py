@@ -44,7 +44,7 @@ SIGNATURES = {
     'smrf_inpaint_setup': (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _i32, _i32, _vp]),
     'smrf_inpaint_start': (_i32, [_vp, _i64, _i64, _i32, _vp, _sz, _i32, _i32, _dbl, _vp, _i32, _vp, _vp, _vp]),
     'smrf_inpaint_step': (_i32, [_i64, _i64, _vp, _sz, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'smrf_inpaint_compact': (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _sz, _i32, _i32, _i64, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'smrf_inpaint_compact': (_i32, [_i32, _vp, _i64, _i64, _i32, _vp, _sz, _i32, _i32, _i64, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'smrf_mg_cycle_part': (_i32, [_i64, _i64, _vp, _sz, _i32, _i32, _i32, _i32, _vp]),
     'smrf_mg_level_layout': (_i32, [_i64, _i64, _i32, C.POINTER(C.c_int64)]),
     'smrf_mg_setup_mask': (_i32, [_vp, _i64, _i64, _vp, _sz, _vp]),

@@ -1248,14 +1248,15 @@ int smrf_inpaint_finish(void* grid, int64_t ny, int64_t nx, int dtype, void* wor
 // The compact solver, one phase at a time, for a row band (neilpy_b200/distributed.py); see include/smrf_b200.h.
 int smrf_inpaint_compact(int op, const void* grid, int64_t ny, int64_t nx, int dtype, void* workspace, size_t workspace_bytes,
                          int has_above, int has_below, int64_t n_unknown, int k, double guess, const void* guess_grid,
-                         const float* z, const double* row_above, const double* row_below, double* out_first,
-                         double* out_last, void* stream) {
+                         const float* z, float* r_plane, const double* row_above, const double* row_below,
+                         double* out_first, double* out_last, void* stream) {
     SMRF_CHECK_ARG(dtype == SMRF_F32 || dtype == SMRF_F64, "bad dtype");
     SMRF_CHECK_ARG(ny > 0 && nx > 0 && ny * nx < ((int64_t)1 << 31), "grid too large for the compact solver");
     SMRF_CHECK_ARG(n_unknown >= 0 && n_unknown <= ny * nx && k >= 0 && k < kMaxIter, "bad n_unknown / iteration");
     Ws w;
     if (int rc = check_ws("smrf_inpaint_compact", workspace, workspace_bytes, ny, nx, has_above, has_below, &w)) return rc;
     SMRF_CHECK_ARG(w.scan_tmp_bytes > 0, "no scan scratch");
+    if (r_plane) w.lev[0].b = r_plane;   // the float32 residual goes straight into the caller's (ghost-extended) plane
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = ny * nx;
     const int nu = (int)n_unknown, ni = (int)n, iy = (int)ny, ix = (int)nx;

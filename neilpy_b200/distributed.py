@@ -38,8 +38,12 @@ COEF_MARGIN = 4        # coefficient rows of the neighbouring bands a band keeps
 
 
 # ------------------------------------------------------------------ partition + halo helpers
-MG_SPLIT = 3          # multigrid levels 0..2 run on the (ghost-extended) band, level 3 and coarser on the global grid
-MG_GHOST = 64         # ghost rows per side for those levels: a multiple of 2**MG_SPLIT, >= their dependency radius (~52)
+# Multigrid levels 0..MG_SPLIT-1 run on the (ghost-extended) band, level MG_SPLIT and coarser on the global grid that
+# every rank holds (replicated work that grows with the number of bands: 1/256 of the cells at split 4).  MG_GHOST =
+# ghost rows per side for the band levels: a multiple of 2**MG_SPLIT and >= their dependency radius, which is
+# (3 + 3 sweeps + restriction + prolongation) * (2**MG_SPLIT - 1) = 120 rows (56 at split 3, where 64 ghost rows do).
+MG_SPLIT = int(os.environ.get('SMRF_MG_SPLIT', 4))
+MG_GHOST = int(os.environ.get('SMRF_MG_GHOST', 128))
 
 
 def rows_per_band(ny, world):
@@ -101,6 +105,28 @@ def raise_together(comm, err, device):
 def _api():
     from . import _lib, api
     return _lib, api
+
+
+class _Sections:
+    """CUDA-event clock for the sections of one CG iteration (SMRF_TIMING_ITER=1; a measuring aid, off by default)."""
+
+    def __init__(self, on):
+        self.on, self.marks = on, []
+
+    def mark(self, name):
+        if self.on:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def totals(self):
+        if not self.on or len(self.marks) < 2:
+            return None
+        torch.cuda.synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return {k: round(v, 3) for k, v in out.items()}
 
 
 def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None, r0=None):
@@ -181,27 +207,38 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
                        full=torch.empty((perL * world, nxL), dtype=torch.float32, device=band.device))
     z_ptr = api._ptr(ext['z']) if ext is not None else None
 
+    sec = _Sections(bool(os.environ.get('SMRF_TIMING_ITER')) and band.is_cuda)
+
     def precondition(k):
         if ext is None:
             _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 0, None, None, None, None, None, st()), 'step0')
             return
         e = ext
-        above, below = exchange_halo(e['band_b0'], e['G'], group)
+        sec.mark('start')
+        own = e['b0E'][e['top']:e['top'] + ny]           # the compact CG kernels write (float) r here themselves
+        if not compact:
+            own.copy_(e['band_b0'])
+        above, below = exchange_halo(own, e['G'], group)
+        sec.mark('halo of r (exchange)')
         if above is not None:
             e['b0E'][:e['top']] = above
-        e['b0E'][e['top']:e['top'] + ny] = e['band_b0']
         if below is not None:
             e['b0E'][e['top'] + ny:] = below
+        sec.mark('halo of r (copies)')
         wE, nE = api._ptr(e['ws']), e['ws'].numel()
         _lib.check(lib.smrf_mg_cycle_part(e['nyE'], nx, wE, nE, e['haE'], e['hbE'], MG_SPLIT, 0, st()), 'mg down')
+        sec.mark('down legs')
         e['mine'][:e['nyL']] = e['bLE'][e['tL']:e['tL'] + e['nyL']]
         comm.all_gather(e['full'], e['mine'])
+        sec.mark('coarse all-gather')
         e['cb'].copy_(e['full'][:e['nyG']])
         _lib.check(lib.smrf_mg_vcycle(e['nyG'], e['nxL'], api._ptr(e['wsC']), e['wsC'].numel(), st()), 'smrf_mg_vcycle')
         e['yLE'].copy_(e['cy'][e['g0']:e['g0'] + e['nyLE']])
+        sec.mark('coarse cycle (global, replicated)')
         # up legs; the level-0 leg adds this band's share of r.z (its owned rows of the extended band) to rz[k]
         _lib.check(lib.smrf_mg_cycle_up_rz(e['nyE'], nx, wE, nE, e['haE'], e['hbE'], MG_SPLIT, api._ptr(rz[k:k + 1]),
                                            e['top'], e['top'] + ny, st()), 'mg up + rz')
+        sec.mark('up legs + r.z')
 
     # With the global preconditioner the CG vectors are COMPACT (this band's NaN cells only, as on one GPU): the
     # V-cycle reads the float32 residual plane the update scatters and hands back z in the grid layout, and only
@@ -211,10 +248,11 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
     if compact:
         rows = torch.empty((4, nx), dtype=torch.float64, device=band.device)
         first, last = rows[0:1], rows[1:2]
+        r_plane = api._ptr(ext['b0E'][ext['top']:ext['top'] + ny])
 
         def cg(op, k=0, z=None, above=None, below=None, outs=False, what='compact'):
             _lib.check(lib.smrf_inpaint_compact(op, bp, ny, nx, code, wp, wn, ha, hb, nu, k, mean,
-                                                api._ptr(guess) if op == 1 else None, z, api._ptr(above), api._ptr(below),
+                                                api._ptr(guess) if op == 1 else None, z, r_plane, api._ptr(above), api._ptr(below),
                                                 api._ptr(first) if outs else None, api._ptr(last) if outs else None, st()),
                        'smrf_inpaint_compact(%s)' % what)
 
@@ -240,12 +278,18 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
             k = it
             precondition(k)
             comm.all_reduce(rz[k:k + 1])
+            sec.mark('all-reduce r.z')
             if compact:
                 cg(4, k, z=z_ptr, outs=True, what='direction')
+                sec.mark('direction')
                 p_above, p_below = comm.exchange(first if ha else None, last if hb else None)
+                sec.mark('rows of p (exchange)')
                 cg(5, k, above=p_above, below=p_below, what='apply')
+                sec.mark('apply')
                 comm.all_reduce(pq[k:k + 1])
+                sec.mark('all-reduce p.q')
                 cg(6, k, what='update')
+                sec.mark('update')
                 it += 1
                 continue
             _lib.check(lib.smrf_inpaint_step(ny, nx, wp, wn, ha, hb, k, 1, z_ptr, None, None, None, None, st()), 'step1')
@@ -269,6 +313,8 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
     else:
         _lib.check(lib.smrf_inpaint_finish(bp, ny, nx, code, wp, wn, st()), 'smrf_inpaint_finish')
     info.update(iterations=it, residual=r)
+    if sec.on:
+        info['sections_ms'] = sec.totals()
     return api._converged(info, tol), ws
 
 
