@@ -38,22 +38,37 @@ COEF_MARGIN = 4        # coefficient rows of the neighbouring bands a band keeps
 
 
 # ------------------------------------------------------------------ partition + halo helpers
-# Multigrid levels 0..MG_SPLIT-1 run on the (ghost-extended) band, level MG_SPLIT and coarser on the global grid that
-# every rank holds (replicated work that grows with the number of bands: 1/256 of the cells at split 4).  MG_GHOST =
-# ghost rows per side for the band levels: a multiple of 2**MG_SPLIT and >= their dependency radius, which is
-# (3 + 3 sweeps + restriction + prolongation) * (2**MG_SPLIT - 1) = 120 rows (56 at split 3, where 64 ghost rows do).
+# Multigrid levels 0..split-1 run on the (ghost-extended) band, level `split` and coarser on the global grid that
+# every rank holds (replicated work that grows with the number of bands: 1/256 of the cells at split 4).  The ghost
+# rows per side are a multiple of 2**split and >= the dependency radius of the band levels, which is
+# (3 + 3 sweeps + restriction + prolongation) * (2**split - 1): 120 rows at split 4, 56 at split 3.
 MG_SPLIT = int(os.environ.get('SMRF_MG_SPLIT', 4))
 MG_GHOST = int(os.environ.get('SMRF_MG_GHOST', 128))
+MG_PLANS = ((MG_SPLIT, MG_GHOST), (3, 64))        # preferred first; the second serves grids whose bands are short
+
+
+def _per(ny, world, split):
+    per = (ny + world - 1) // world
+    if world > 1:
+        q = 1 << split
+        per = (per + q - 1) // q * q
+    return per
+
+
+def mg_plan(ny, world):
+    """(split, ghost rows) for a grid of `ny` rows cut into `world` bands: the first of MG_PLANS whose ghost rows
+    every band (the last one is the shortest) can serve to its neighbours."""
+    for split, ghost in MG_PLANS:
+        per = _per(ny, world, split)
+        if world == 1 or ny - (world - 1) * per >= ghost:
+            return split, ghost
+    return MG_PLANS[-1]
 
 
 def rows_per_band(ny, world):
-    """Equal bands; with several ranks a multiple of 2**MG_SPLIT rows so that the cells of the
-    first global multigrid level never straddle two bands."""
-    per = (ny + world - 1) // world
-    if world > 1:
-        q = 1 << MG_SPLIT
-        per = (per + q - 1) // q * q
-    return per
+    """Equal bands; with several ranks a multiple of 2**split rows (split = mg_plan(ny, world)[0]) so that the
+    cells of the first global multigrid level never straddle two bands."""
+    return _per(ny, world, mg_plan(ny, world)[0])
 
 
 def band_bounds(ny, world, rank):
@@ -129,7 +144,7 @@ class _Sections:
         return {k: round(v, 3) for k, v in out.items()}
 
 
-def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None, r0=None):
+def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None, r0=None, mg=None):
     """Distributed multigrid-preconditioned CG on a row band (see module docstring)."""
     _lib, api = _api()
     comm = group = as_comm(group)
@@ -169,8 +184,8 @@ def _inpaint_band(lib, band, ws, tol, group, max_iter=4000, guess=None, per=None
     # on a hierarchy of the global coarse grid that every rank holds.
     ext = None
     lv = (C.c_int64 * 6)()
+    MG_SPLIT, G = mg if mg is not None else MG_PLANS[0]
     if world > 1 and per is not None and r0 is not None:
-        G = MG_GHOST
         mE, top = with_halo(m, G, group)
         mE = mE.contiguous()
         nyE = mE.shape[0]
@@ -517,7 +532,8 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     nx, ny = len(xedges) - 1, len(yedges) - 1
     mark('extent')
     wmax = int(windows.max()) if len(windows) else 1
-    check_partition(ny, world, max(2 * wmax, SPLINE_HALO, MG_GHOST))
+    mg = mg_plan(ny, world)
+    check_partition(ny, world, max(2 * wmax, SPLINE_HALO, mg[1]))
     t = api._make_transform(xedges[0], yedges[0], cellsize)
     inv6 = api._inverse6(t)
     per = rows_per_band(ny, world)
@@ -542,7 +558,7 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     mark('binning')
 
     # ---- inpaint, low outliers, progressive filter, punch, inpaint
-    info1, ws = _inpaint_band(lib, Zmin, None, tol, group, per=per, r0=r0)
+    info1, ws = _inpaint_band(lib, Zmin, None, tol, group, per=per, r0=r0, mg=mg)
     mark('inpaint1')
     low = torch.zeros((rows, nx), dtype=torch.uint8, device=dev)
     one = np.array([1])
@@ -557,7 +573,7 @@ def smrf_sharded(points, cellsize=1, windows=5, slope_threshold=.15, elevation_t
     _lib.check(lib.smrf_merge_punch(api._ptr(Zmin), api._ptr(empty), api._ptr(low), api._ptr(obj),
                                     api._ptr(object_cells), rows, nx, code, st()), 'smrf_merge_punch')
     Zpro = Zmin
-    info2, ws = _inpaint_band(lib, Zpro, ws, tol, group, guess=opened, per=per, r0=r0)
+    info2, ws = _inpaint_band(lib, Zpro, ws, tol, group, guess=opened, per=per, r0=r0, mg=mg)
     del opened
     del ws
     mark('inpaint2')

@@ -19,10 +19,24 @@ def test_band_bounds_cover_the_grid():
         assert edges[0][0] == 0 and edges[-1][1] == ny
         assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
         assert max(b - a for a, b in edges) <= D.rows_per_band(ny, world)
-        assert world == 1 or D.rows_per_band(ny, world) % (1 << D.MG_SPLIT) == 0   # coarse cells never straddle bands
+        split, ghost = D.mg_plan(ny, world)
+        assert world == 1 or D.rows_per_band(ny, world) % (1 << split) == 0   # coarse cells never straddle bands
     with pytest.raises(ValueError):
         D.check_partition(100, 4, 40)
     D.check_partition(5001, 8, 80)
+
+
+def test_multigrid_plan_fits_the_shortest_band():
+    # (rows, bands): the bench grids at 2..8 GPUs, BASELINE configs[3], and the small parity grid of bench.py
+    for ny, world in [(10001, 2), (14143, 4), (20001, 8), (44723, 8), (1416, 2), (1416, 4), (1416, 8), (5001, 8)]:
+        split, ghost = D.mg_plan(ny, world)
+        assert (split, ghost) in D.MG_PLANS and ghost % (1 << split) == 0
+        assert ghost >= 8 * ((1 << split) - 1)                # dependency radius of the band levels
+        r0, r1 = D.band_bounds(ny, world, world - 1)
+        assert r1 - r0 >= ghost, (ny, world, split, ghost)    # the last band is the shortest
+        D.check_partition(ny, world, ghost)
+    assert D.mg_plan(20001, 8) == D.MG_PLANS[0]
+    assert D.mg_plan(1416, 8) == (3, 64)                      # 1416 - 7 * 192 = 72 rows could not serve 128
 
 
 def test_window_chunks():

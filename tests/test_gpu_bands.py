@@ -25,12 +25,16 @@ def _sharded(xyzw, world, kw, slices=None):
     return run_virtual_ranks(world, lambda comm: smrf_sharded(parts[comm.rank], gather=True, comm=comm, **kw), dev), slices
 
 
-@pytest.mark.parametrize('world', [2, 4])
-def test_virtual_bands_equal_unsharded(world):
+# (bands, extent): two and four bands; eight bands on a grid whose last band (1417 - 7 * 192 = 73 rows) cannot serve
+# the 128 ghost rows of the preferred multigrid split, so that the (3, 64) plan runs; eight bands with the (4, 128) plan
+@pytest.mark.parametrize('world,ex,ey', [(2, 500.0, 700.0), (4, 500.0, 700.0), (8, 300.0, 1416.0), (8, 250.0, 2100.0)])
+def test_virtual_bands_equal_unsharded(world, ex, ey):
     import torch
     import neilpy_b200 as nb
+    from neilpy_b200.distributed import mg_plan, MG_PLANS
     from neilpy_b200.synth import synth_cloud
-    x, y, z, _ = synth_cloud(700000, 500.0, 700.0, seed=11)
+    x, y, z, _ = synth_cloud(int(ex * ey * 2), ex, ey, seed=11)
+    assert mg_plan(int(ey) + 1, world) == (MG_PLANS[1] if ey == 1416.0 else MG_PLANS[0])
     xyzw = np.stack([x, y, z, np.zeros_like(x)], 1).astype(np.float32)
     st = {}
     Z1, t1, oc1, op1 = nb.smrf(torch.as_tensor(xyzw).cuda(), return_stages=st, **KW)
