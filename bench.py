@@ -172,13 +172,17 @@ def run_reference(args):
 def workload_config(args):
     ex, ey = extent_for(args.points)
     return {'workload': 'BASELINE.json configs[1]: synthetic terrain+buildings+vegetation cloud, %d points per GPU, '
-                        '%.0f m x %.0f m, cellsize=1, windows=18 (slope .15, elev .5, scaler 1.25)'
-                        % (args.points, ex, ey),
+                        '%.0f m x %.0f m%s, cellsize=1, windows=18 (slope .15, elev .5, scaler 1.25)'
+                        % (args.points, ex, ey * args.gpus,
+                           ' (one %.0f m square per GPU stacked along y; every rank holds points of the whole area)' % ex
+                           if args.gpus > 1 else ''),
             'points_per_gpu': args.points, 'cellsize': 1, 'windows': 18,
             'l2': 'inputs larger than L2 (point stream %.0f MB, grid planes %.0f MB each)'
                   % (args.points * 16 / 1e6, (ex + 1) * (ey + 1) * 4 / 1e6),
-            'parallelism': ('row bands x%d: reduce-scatter(min) binning, 2w-row halo exchange per window, '
-                            'CG with all-reduced dot products, all-gathered spline coefficients' % args.gpus)
+            'parallelism': ('row bands x%d: points routed once to the rank owning their row (all-to-all), band-local '
+                            'binning and classification, grouped 2w-row halo exchange per window group, compact CG with '
+                            'all-reduced dot products preconditioned by the exact global V-cycle (ghost-extended band '
+                            'levels + replicated coarse levels), 80-row spline halo' % args.gpus)
             if args.gpus > 1 else 'single GPU'}
 
 
