@@ -8,9 +8,11 @@ the single-GPU path (and the reference) produces for the whole cloud:
   extent        all-reduce(min/max) of 4 doubles
   binning       every point travels once to the rank that owns its row band (all-to-all of the
                 point records, csrc/route.cu); binning is then band-local
-  inpaint       conjugate gradients over all bands (all-reduce of the two dot products and
-                one boundary row of the search direction per iteration); each band is
-                preconditioned by its own multigrid V-cycle (block Jacobi over bands)
+  inpaint       conjugate gradients over all bands on compact vectors (a band's NaN cells only):
+                all-reduce of the two dot products and one boundary row of the search direction
+                per iteration; the preconditioner is the exact GLOBAL multigrid V-cycle (fine
+                levels on the ghost-extended band, coarse levels on a replicated global grid), so
+                the iteration is the single-GPU one
   opening       before window w every band receives 2w rows of the previous window's
                 surface from each neighbour (erosion needs w, the dilation of it another w)
   slope         1 halo row

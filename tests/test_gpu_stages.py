@@ -312,6 +312,18 @@ def test_inpaint_edge_cases(nb):
     assert np.allclose(nb.inpaint_nans_by_springs(one), [[1.0, 2.0, 3.0]], atol=1e-9)
 
 
+def test_inpaint_reports_a_non_finite_residual(nb):
+    """an inf elevation next to a hole must not read as a converged solve (the residual max keeps
+    NaN / inf), and the caller is told."""
+    from neilpy_b200.api import InpaintWarning
+    A = surface(40, 52, 3)
+    A[10:14, 20:30] = np.nan
+    A[9, 22] = np.inf
+    with pytest.warns(InpaintWarning, match='non-finite'):
+        _, info = nb.inpaint_nans_by_springs(A, return_info=True)
+    assert not info['converged'] and not np.isfinite(info['residual'])
+
+
 def test_inpaint_isprs_sparse_sample(nb):
     x, y, z, _ = load_isprs('samp53')                 # 82 % empty cells, LSQR needs 333 iterations
     I, _ = O.create_dem(x, y, z, 1, 'min')

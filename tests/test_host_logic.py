@@ -119,3 +119,17 @@ def test_threaded_host_copy(monkeypatch):
     one = api._copy_threads()
     monkeypatch.setenv('LOCAL_WORLD_SIZE', '64')
     assert 1 <= api._copy_threads() <= one <= 4
+
+
+def test_inpaint_convergence_is_reported():
+    """a solve that ends above its tolerance, or with a non-finite residual, warns and says so in `info`."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('error')                      # the converged cases must not warn
+        assert api._converged({'iterations': 5, 'residual': 1e-9, 'unknown': 10}, 1e-6)['converged']
+        assert api._converged({'iterations': 0, 'residual': float('nan'), 'unknown': 0}, 1e-6)['converged']   # nothing to solve
+    with pytest.warns(api.InpaintWarning, match='tolerance'):
+        assert not api._converged({'iterations': 4000, 'residual': 1e-3, 'unknown': 10}, 1e-6)['converged']
+    for bad in (float('inf'), float('nan')):
+        with pytest.warns(api.InpaintWarning, match='non-finite'):
+            assert not api._converged({'iterations': 1, 'residual': bad, 'unknown': 10}, 1e-6)['converged']
